@@ -1,0 +1,229 @@
+"""Drop-in for the reference's ``cross_atten/mamba.py``: same classes, constructor arguments, parameter
+names/shapes (state-dict compatible) and call signatures; the work under ``MambaBlock`` is done by the
+sm_100a kernels behind ``gfe_mamba_b200.ops``.
+
+What stays in torch (by design): the four projections (cuBLAS GEMMs), RMSNorm and the residual add.
+What moved into hand-written CUDA: causal depthwise conv + SiLU, softplus(+bias), discretisation, the scan,
+the C contraction, the D skip, the SiLU(z) gate, their backward passes, and the decode step.
+
+Reference line numbers below refer to cross_atten/mamba.py of Tinysqua/GFE-Mamba.
+"""
+import math
+from dataclasses import dataclass
+from typing import Union
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .pscan import pscan
+
+
+@dataclass
+class MambaConfig:
+    """Field-for-field the reference's dataclass (mamba.py:31-59)."""
+    d_model: int  # D
+    n_layers: int
+    dt_rank: Union[int, str] = 'auto'
+    d_state: int = 16  # N
+    expand_factor: int = 2  # E
+    d_conv: int = 4
+
+    dt_min: float = 0.001
+    dt_max: float = 0.1
+    dt_init: str = "random"  # "random" or "constant"
+    dt_scale: float = 1.0
+    dt_init_floor = 1e-4  # un-annotated in the reference too: a class attribute, not a field (mamba.py:44)
+
+    rms_norm_eps: float = 1e-5
+
+    bias: bool = False
+    conv_bias: bool = True
+    inner_layernorms: bool = False
+
+    pscan: bool = True  # kept for API compatibility; both modes run the same fused kernel here
+    use_cuda: bool = False  # accepted (mamba_transformer.py:65 passes True); never needs mamba_ssm here
+
+    def __post_init__(self):
+        self.d_inner = self.expand_factor * self.d_model  # ED
+
+        if self.dt_rank == 'auto':
+            self.dt_rank = math.ceil(self.d_model / 16)
+
+
+class Mamba(nn.Module):
+    """mamba.py:61-89."""
+
+    def __init__(self, config: MambaConfig):
+        super().__init__()
+        self.config = config
+        self.layers = nn.ModuleList([ResidualBlock(config) for _ in range(config.n_layers)])
+
+    def forward(self, x):
+        # x : (B, L, D) -> (B, L, D)
+        for layer in self.layers:
+            x = layer(x)
+        return x
+
+    def step(self, x, caches):
+        # x : (B, D); caches : [(h, inputs)] per layer
+        for i, layer in enumerate(self.layers):
+            x, caches[i] = layer.step(x, caches[i])
+        return x, caches
+
+
+class ResidualBlock(nn.Module):
+    """mamba.py:91-117: output = mixer(norm(x)) + x."""
+
+    def __init__(self, config: MambaConfig):
+        super().__init__()
+        self.mixer = MambaBlock(config)
+        self.norm = RMSNorm(config.d_model, config.rms_norm_eps)
+
+    def forward(self, x):
+        return self.mixer(self.norm(x)) + x
+
+    def step(self, x, cache):
+        output, cache = self.mixer.step(self.norm(x), cache)
+        return output + x, cache
+
+
+class MambaBlock(nn.Module):
+    """mamba.py:119-405.  Parameter creation order and initialisation are the reference's (mamba.py:126-168) so
+    a seeded construction draws the same values and reference checkpoints load with strict=True."""
+
+    def __init__(self, config: MambaConfig):
+        super().__init__()
+        self.config = config
+
+        self.in_proj = nn.Linear(config.d_model, 2 * config.d_inner, bias=config.bias)
+        self.conv1d = nn.Conv1d(in_channels=config.d_inner, out_channels=config.d_inner,
+                                kernel_size=config.d_conv, bias=config.conv_bias,
+                                groups=config.d_inner, padding=config.d_conv - 1)
+        self.x_proj = nn.Linear(config.d_inner, config.dt_rank + 2 * config.d_state, bias=False)
+        self.dt_proj = nn.Linear(config.dt_rank, config.d_inner, bias=True)
+
+        dt_init_std = config.dt_rank ** -0.5 * config.dt_scale
+        if config.dt_init == "constant":
+            nn.init.constant_(self.dt_proj.weight, dt_init_std)
+        elif config.dt_init == "random":
+            nn.init.uniform_(self.dt_proj.weight, -dt_init_std, dt_init_std)
+        else:
+            raise NotImplementedError
+
+        dt = torch.exp(
+            torch.rand(config.d_inner) * (math.log(config.dt_max) - math.log(config.dt_min)) + math.log(config.dt_min)
+        ).clamp(min=config.dt_init_floor)
+        inv_dt = dt + torch.log(-torch.expm1(-dt))  # inverse softplus
+        with torch.no_grad():
+            self.dt_proj.bias.copy_(inv_dt)
+
+        A = torch.arange(1, config.d_state + 1, dtype=torch.float32).repeat(config.d_inner, 1)
+        self.A_log = nn.Parameter(torch.log(A))
+        self.A_log._no_weight_decay = True
+
+        self.D = nn.Parameter(torch.ones(config.d_inner))
+        self.D._no_weight_decay = True
+
+        self.out_proj = nn.Linear(config.d_inner, config.d_model, bias=config.bias)
+
+        if self.config.inner_layernorms:
+            self.dt_layernorm = RMSNorm(self.config.dt_rank, config.rms_norm_eps)
+            self.B_layernorm = RMSNorm(self.config.d_state, config.rms_norm_eps)
+            self.C_layernorm = RMSNorm(self.config.d_state, config.rms_norm_eps)
+        else:
+            self.dt_layernorm = None
+            self.B_layernorm = None
+            self.C_layernorm = None
+        # config.use_cuda is accepted as-is: the fused sm_100a kernel *is* the CUDA path (no mamba_ssm import,
+        # no fallback message, mamba.py:179-186).
+
+    def _apply_layernorms(self, dt, B, C):
+        if self.dt_layernorm is not None:
+            dt = self.dt_layernorm(dt)
+        if self.B_layernorm is not None:
+            B = self.B_layernorm(B)
+        if self.C_layernorm is not None:
+            C = self.C_layernorm(C)
+        return dt, B, C
+
+    # ------------------------------------------------------------------ training / prefill
+    def forward(self, x):
+        # x : (B, L, D) -> (B, L, D)          mamba.py:197-225
+        xz = self.in_proj(x)                                  # (B, L, 2*ED)   GEMM
+        xin, z = xz.chunk(2, dim=-1)                          # strided halves, consumed in place by the kernels
+        u = ops.causal_conv1d_silu(xin, self.conv1d.weight, self.conv1d.bias)   # conv + bias + SiLU fused (:208-212)
+        y = self._ssm_fused(u, z)                             # scan + D skip + SiLU(z) gate fused (:213-222)
+        return self.out_proj(y)                               # GEMM
+
+    def _project(self, x):
+        """x_proj / split / optional layernorms / dt_proj without bias (mamba.py:235-238).  delta comes out
+        channel-last (B, L, ED); the reference forms the same product as W @ delta^T."""
+        deltaBC = self.x_proj(x)
+        delta, B, C = torch.split(deltaBC, [self.config.dt_rank, self.config.d_state, self.config.d_state], dim=-1)
+        delta, B, C = self._apply_layernorms(delta, B, C)
+        delta = F.linear(delta, self.dt_proj.weight)
+        return delta, B, C
+
+    def _ssm_fused(self, x, z):
+        delta, B, C = self._project(x)
+        if self.config.d_state == 16:
+            return ops.selective_scan_fn(x, delta, self.A_log, B, C, self.D, z=z, dt_bias=self.dt_proj.bias,
+                                         delta_softplus=True)
+        # other state sizes: the reference's own composition on top of the CUDA pscan kernel
+        delta = F.softplus(delta + self.dt_proj.bias)
+        y = self.selective_scan(x, delta, -torch.exp(self.A_log.float()), B, C, self.D.float())
+        return y if z is None else y * F.silu(z)
+
+    def ssm(self, x, z):
+        """mamba.py:227-263.  As in the reference the gate is applied here only when ``config.use_cuda`` is set
+        (mamba.py:243-252); otherwise ``forward`` owns it.  ``forward`` itself always uses the fused form."""
+        return self._ssm_fused(x, z if self.config.use_cuda else None)
+
+    def selective_scan(self, x, delta, A, B, C, D):
+        """mamba.py:265-286: x, delta (B, L, ED) with delta already softplus'ed; A (ED, N) negative; B, C (B, L, N);
+        D (ED) -> y (B, L, ED) without gate."""
+        if A.shape[1] == 16:
+            return ops.selective_scan_fn(x, delta, torch.log(-A), B, C, D, z=None, dt_bias=None, delta_softplus=False)
+        deltaA = torch.exp(delta.unsqueeze(-1) * A)           # (B, L, ED, N)
+        BX = (delta.unsqueeze(-1) * B.unsqueeze(2)) * x.unsqueeze(-1)
+        hs = pscan(deltaA, BX)
+        y = (hs @ C.unsqueeze(-1)).squeeze(3)
+        return y + D * x
+
+    def selective_scan_seq(self, x, delta, A, B, C, D):
+        """mamba.py:288-318.  The reference's sequential mode is a second formulation of the same recurrence; on
+        the GPU both names run the same sequential-in-time kernel."""
+        return self.selective_scan(x, delta, A, B, C, D)
+
+    # ------------------------------------------------------------------ decode
+    def step(self, x, cache):
+        # x : (B, D); cache : (h (B, ED, N) or None, inputs (B, ED, d_conv-1))      mamba.py:342-373
+        h, inputs = cache
+        xz = self.in_proj(x)                                  # (B, 2*ED)
+        xin, z = xz.chunk(2, dim=1)
+        u, inputs = ops.conv1d_step(xin, inputs, self.conv1d.weight, self.conv1d.bias)
+        y, h = self.ssm_step(u, h, z=z)
+        output = self.out_proj(y)
+        return output, (h, inputs)
+
+    def ssm_step(self, x, h, z=None):
+        """mamba.py:375-405 (+ the gate of :364-367 when ``z`` is given).  Returns (y, h_new)."""
+        deltaBC = self.x_proj(x)
+        delta, B, C = torch.split(deltaBC, [self.config.dt_rank, self.config.d_state, self.config.d_state], dim=-1)
+        delta, B, C = self._apply_layernorms(delta, B, C)
+        delta = F.linear(delta, self.dt_proj.weight)
+        return ops.ssm_step(x, delta, self.A_log, B, C, self.D, h, z=z, dt_bias=self.dt_proj.bias, delta_softplus=True)
+
+
+class RMSNorm(nn.Module):
+    """mamba.py:408-418."""
+
+    def __init__(self, d_model: int, eps: float = 1e-5):
+        super().__init__()
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(d_model))
+
+    def forward(self, x):
+        return x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + self.eps) * self.weight

@@ -1,0 +1,314 @@
+"""torch.autograd wrappers around the C ABI (include/gfe_mamba_b200.h).
+
+PyTorch is plumbing here: it owns device memory, streams and autograd bookkeeping; every number is
+produced by the sm_100a kernels in csrc/.  CPU tensors are rejected -- there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _native as nat
+
+_DT = {torch.float32: nat.GFE_F32, torch.bfloat16: nat.GFE_BF16, torch.float16: nat.GFE_F16}
+
+
+def _require_cuda(*ts: Optional[torch.Tensor]) -> torch.device:
+    dev = None
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("gfe_mamba_b200: CUDA tensors required (this library has no CPU fallback); "
+                               f"got a tensor on {t.device}")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"gfe_mamba_b200: tensors on different devices ({dev} vs {t.device})")
+    return dev
+
+
+def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream(dev: torch.device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _bytes(n: int, dev: torch.device) -> Optional[torch.Tensor]:
+    return torch.empty(n, dtype=torch.uint8, device=dev) if n > 0 else None
+
+
+def _rows(t: torch.Tensor) -> torch.Tensor:
+    """(B, L, C) with unit channel stride; batch/row strides are passed to the kernels as they are."""
+    return t if t.stride(-1) == 1 else t.contiguous()
+
+
+def _f32(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    return t.detach().float().contiguous()
+
+
+# ------------------------------------------------------------------------------------------ pscan
+class _PScanFn(torch.autograd.Function):
+    """pscan(A, X) -- cross_atten/pscan.py:152-224 (PScan.forward / PScan.backward)."""
+
+    @staticmethod
+    def forward(ctx, A_in: torch.Tensor, X_in: torch.Tensor) -> torch.Tensor:
+        dev = _require_cuda(A_in, X_in)
+        if A_in.dim() != 4 or A_in.shape != X_in.shape:
+            raise ValueError(f"pscan expects A, X of identical shape (B, L, D, N); got {tuple(A_in.shape)}, {tuple(X_in.shape)}")
+        A = A_in.detach().float().contiguous()
+        X = X_in.detach().float().contiguous()
+        B, L, D, N = A.shape
+        H = torch.empty_like(X)
+        l = nat.lib()
+        with torch.cuda.device(dev):
+            nws = l.gfe_pscan_workspace_bytes(B, L, D, N)
+            ws = _bytes(nws, dev)
+            nat.check(l.gfe_pscan_fwd(_ptr(A), _ptr(X), _ptr(H), B, L, D, N, _ptr(ws), nws, _stream(dev)), "pscan_fwd")
+        ctx.save_for_backward(A, H)
+        ctx.in_dtypes = (A_in.dtype, X_in.dtype)
+        return H if X_in.dtype == torch.float32 else H.to(X_in.dtype)
+
+    @staticmethod
+    def backward(ctx, dH_in: torch.Tensor):
+        A, H = ctx.saved_tensors
+        dev = A.device
+        dH = dH_in.detach().float().contiguous()
+        B, L, D, N = A.shape
+        dA, dX = torch.empty_like(A), torch.empty_like(A)
+        l = nat.lib()
+        with torch.cuda.device(dev):
+            nws = l.gfe_pscan_workspace_bytes(B, L, D, N)
+            ws = _bytes(nws, dev)
+            nat.check(l.gfe_pscan_bwd(_ptr(A), _ptr(H), _ptr(dH), _ptr(dA), _ptr(dX), B, L, D, N, _ptr(ws), nws, _stream(dev)),
+                      "pscan_bwd")
+        return dA.to(ctx.in_dtypes[0]), dX.to(ctx.in_dtypes[1])
+
+
+def pscan(A: torch.Tensor, X: torch.Tensor) -> torch.Tensor:
+    """H[t] = A[t] * H[t-1] + X[t] over dim 1 of (B, L, D, N) tensors; differentiable in both arguments."""
+    return _PScanFn.apply(A, X)
+
+
+# ------------------------------------------------------------------------------- selective scan
+def _fill_common(a: nat.SelscanArgs, u, delta, z, Bm, Cm, A_log, D, dt_bias, softplus: bool):
+    B, L, ED = u.shape
+    a.batch, a.seqlen, a.d_inner, a.d_state = B, L, ED, A_log.shape[1]
+    a.dtype = _DT[u.dtype]
+    a.flags = nat.GFE_FLAG_DELTA_SOFTPLUS if softplus else 0
+    a.u, a.u_bs, a.u_rs = u.data_ptr(), u.stride(0), u.stride(1)
+    a.delta, a.delta_bs, a.delta_rs = delta.data_ptr(), delta.stride(0), delta.stride(1)
+    if z is not None:
+        a.z, a.z_bs, a.z_rs = z.data_ptr(), z.stride(0), z.stride(1)
+    a.Bm, a.B_bs, a.B_rs = Bm.data_ptr(), Bm.stride(0), Bm.stride(1)
+    a.Cm, a.C_bs, a.C_rs = Cm.data_ptr(), Cm.stride(0), Cm.stride(1)
+    a.A_log, a.D = A_log.data_ptr(), D.data_ptr()
+    a.dt_bias = 0 if dt_bias is None else dt_bias.data_ptr()
+
+
+class _SelectiveScanFn(torch.autograd.Function):
+    """Fused MambaBlock.ssm tail: softplus(delta + bias) -> discretise -> scan -> C contraction -> D skip -> * silu(z)
+    (cross_atten/mamba.py:255-256, 265-286, 220-222; the contract of the selective_scan_fn call at mamba.py:251)."""
+
+    @staticmethod
+    def forward(ctx, u, delta, A_log, Bm, Cm, D, z, dt_bias, softplus: bool, return_last_state: bool):
+        dev = _require_cuda(u, delta, A_log, Bm, Cm, D, z, dt_bias)
+        if u.dim() != 3:
+            raise ValueError(f"selective_scan: u must be (B, L, ED); got {tuple(u.shape)}")
+        B, L, ED = u.shape
+        N = A_log.shape[1]
+        if u.dtype not in _DT:
+            raise TypeError(f"selective_scan: unsupported activation dtype {u.dtype}")
+        if tuple(delta.shape) != (B, L, ED) or tuple(Bm.shape) != (B, L, N) or tuple(Cm.shape) != (B, L, N) \
+                or tuple(A_log.shape) != (ED, N) or tuple(D.shape) != (ED,):
+            raise ValueError("selective_scan: inconsistent shapes")
+        dt = u.dtype
+        u_, delta_, Bm_, Cm_ = (_rows(t.detach().to(dt)) for t in (u, delta, Bm, Cm))
+        z_ = None if z is None else _rows(z.detach().to(dt))
+        A_log_, D_, bias_ = _f32(A_log), _f32(D), _f32(dt_bias)
+        out = torch.empty((B, L, ED), dtype=dt, device=dev)
+        last = torch.empty((B, ED, N), dtype=torch.float32, device=dev) if return_last_state else None
+        need_grad = any(ctx.needs_input_grad)
+        l = nat.lib()
+        a = nat.SelscanArgs()
+        _fill_common(a, u_, delta_, z_, Bm_, Cm_, A_log_, D_, bias_, softplus)
+        a.out, a.out_bs, a.out_rs = out.data_ptr(), out.stride(0), out.stride(1)
+        a.last_state = 0 if last is None else last.data_ptr()
+        with torch.cuda.device(dev):
+            nck = l.gfe_selscan_ckpt_bytes(B, L, ED, N) if need_grad else 0
+            ckpt = _bytes(nck, dev)
+            nws = l.gfe_selscan_fwd_workspace_bytes(B, L, ED, N)
+            ws = _bytes(nws, dev)
+            a.ckpt, a.ckpt_bytes = (0 if ckpt is None else ckpt.data_ptr()), nck
+            a.ws, a.ws_bytes = (0 if ws is None else ws.data_ptr()), nws
+            nat.check(l.gfe_selscan_fwd(ctypes.byref(a), _stream(dev)), "selscan_fwd")
+        if need_grad:
+            ctx.save_for_backward(u_, delta_, A_log_, Bm_, Cm_, D_, z_, bias_, ckpt)
+            ctx.softplus = softplus
+            ctx.in_dtypes = tuple(None if t is None else t.dtype for t in (u, delta, A_log, Bm, Cm, D, z, dt_bias))
+        if return_last_state:
+            ctx.mark_non_differentiable(last)
+            return out, last
+        return out
+
+    @staticmethod
+    def backward(ctx, dout, *unused):
+        u, delta, A_log, Bm, Cm, D, z, bias, ckpt = ctx.saved_tensors
+        dev = u.device
+        B, L, ED = u.shape
+        N = A_log.shape[1]
+        dt = u.dtype
+        dout = _rows(dout.detach().to(dt))
+        du = torch.empty((B, L, ED), dtype=dt, device=dev)
+        ddelta = torch.empty((B, L, ED), dtype=dt, device=dev)
+        dz = None if z is None else torch.empty((B, L, ED), dtype=dt, device=dev)
+        dBm = torch.empty((B, L, N), dtype=dt, device=dev)
+        dCm = torch.empty((B, L, N), dtype=dt, device=dev)
+        dA_log = torch.empty((ED, N), dtype=torch.float32, device=dev)
+        dD = torch.empty((ED,), dtype=torch.float32, device=dev)
+        dbias = None if bias is None else torch.empty((ED,), dtype=torch.float32, device=dev)
+        l = nat.lib()
+        a = nat.SelscanArgs()
+        _fill_common(a, u, delta, z, Bm, Cm, A_log, D, bias, ctx.softplus)
+        a.ckpt, a.ckpt_bytes = ckpt.data_ptr(), ckpt.numel()
+        a.dout, a.dout_bs, a.dout_rs = dout.data_ptr(), dout.stride(0), dout.stride(1)
+        a.du, a.du_bs, a.du_rs = du.data_ptr(), du.stride(0), du.stride(1)
+        a.ddelta, a.ddelta_bs, a.ddelta_rs = ddelta.data_ptr(), ddelta.stride(0), ddelta.stride(1)
+        if dz is not None:
+            a.dz, a.dz_bs, a.dz_rs = dz.data_ptr(), dz.stride(0), dz.stride(1)
+        a.dBm, a.dB_bs, a.dB_rs = dBm.data_ptr(), dBm.stride(0), dBm.stride(1)
+        a.dCm, a.dC_bs, a.dC_rs = dCm.data_ptr(), dCm.stride(0), dCm.stride(1)
+        a.dA_log, a.dD = dA_log.data_ptr(), dD.data_ptr()
+        a.ddt_bias = 0 if dbias is None else dbias.data_ptr()
+        with torch.cuda.device(dev):
+            nws = l.gfe_selscan_bwd_workspace_bytes(B, L, ED, N)
+            ws = _bytes(nws, dev)
+            a.ws, a.ws_bytes = (0 if ws is None else ws.data_ptr()), nws
+            nat.check(l.gfe_selscan_bwd(ctypes.byref(a), _stream(dev)), "selscan_bwd")
+        dts = ctx.in_dtypes
+
+        def cast(g, i):
+            return None if (g is None or dts[i] is None) else (g if g.dtype == dts[i] else g.to(dts[i]))
+
+        return (cast(du, 0), cast(ddelta, 1), cast(dA_log, 2), cast(dBm, 3), cast(dCm, 4), cast(dD, 5),
+                cast(dz, 6), cast(dbias, 7), None, None)
+
+
+def selective_scan_fn(u: torch.Tensor, delta: torch.Tensor, A_log: torch.Tensor, Bm: torch.Tensor, Cm: torch.Tensor,
+                      D: torch.Tensor, z: Optional[torch.Tensor] = None, dt_bias: Optional[torch.Tensor] = None,
+                      delta_softplus: bool = True, return_last_state: bool = False):
+    """Fused selective scan, channel-last.
+
+    u, delta, z: (B, L, ED) (any batch/row strides, unit channel stride); Bm, Cm: (B, L, N); A_log: (ED, N);
+    D, dt_bias: (ED).  Returns out (B, L, ED) in u's dtype:
+        delta' = softplus(delta + dt_bias);  h_t = exp(delta' A) h_{t-1} + delta' B_t u_t,  A = -exp(A_log)
+        out_t  = (C_t . h_t + D u_t) * silu(z_t)
+    """
+    return _SelectiveScanFn.apply(u, delta, A_log, Bm, Cm, D, z, dt_bias, bool(delta_softplus), bool(return_last_state))
+
+
+# ----------------------------------------------------------------------- causal conv1d + SiLU
+class _CausalConv1dSiluFn(torch.autograd.Function):
+    """silu(Conv1d(groups=ED, k=K, padding=K-1)(x^T)[:, :, :L]^T) -- cross_atten/mamba.py:128-131, 208-212."""
+
+    @staticmethod
+    def forward(ctx, xin, weight, bias):
+        dev = _require_cuda(xin, weight, bias)
+        if xin.dim() != 3:
+            raise ValueError(f"causal_conv1d_silu: x must be (B, L, ED); got {tuple(xin.shape)}")
+        B, L, ED = xin.shape
+        K = weight.shape[-1]
+        if weight.numel() != ED * K:
+            raise ValueError("causal_conv1d_silu: weight must be (ED, 1, K) / (ED, K)")
+        x_ = _rows(xin.detach())
+        w_ = weight.detach().float().reshape(ED, K).contiguous()
+        b_ = _f32(bias)
+        u = torch.empty((B, L, ED), dtype=xin.dtype, device=dev)
+        l = nat.lib()
+        with torch.cuda.device(dev):
+            nat.check(l.gfe_conv1d_silu_fwd(_ptr(x_), x_.stride(0), x_.stride(1), _ptr(w_), _ptr(b_), _ptr(u), u.stride(0),
+                                            u.stride(1), B, L, ED, K, _DT[xin.dtype], _stream(dev)), "conv1d_silu_fwd")
+        ctx.save_for_backward(x_, w_, b_)
+        ctx.meta = (weight.shape, weight.dtype, None if bias is None else bias.dtype)
+        return u
+
+    @staticmethod
+    def backward(ctx, du):
+        x_, w_, b_ = ctx.saved_tensors
+        dev = x_.device
+        B, L, ED = x_.shape
+        K = w_.shape[1]
+        du = _rows(du.detach().to(x_.dtype))
+        dx = torch.empty((B, L, ED), dtype=x_.dtype, device=dev)
+        dw = torch.empty((ED, K), dtype=torch.float32, device=dev)
+        db = None if b_ is None else torch.empty((ED,), dtype=torch.float32, device=dev)
+        l = nat.lib()
+        with torch.cuda.device(dev):
+            nws = l.gfe_conv1d_bwd_workspace_bytes(B, L, ED, K)
+            ws = _bytes(nws, dev)
+            nat.check(l.gfe_conv1d_silu_bwd(_ptr(x_), x_.stride(0), x_.stride(1), _ptr(w_), _ptr(b_), _ptr(du), du.stride(0),
+                                            du.stride(1), _ptr(dx), dx.stride(0), dx.stride(1), _ptr(dw), _ptr(db),
+                                            B, L, ED, K, _DT[x_.dtype], _ptr(ws), nws, _stream(dev)), "conv1d_silu_bwd")
+        wshape, wdt, bdt = ctx.meta
+        return dx, dw.reshape(wshape).to(wdt), (None if db is None else db.to(bdt))
+
+
+def causal_conv1d_silu(xin: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """Channel-last causal depthwise conv + bias + SiLU.  xin: (B, L, ED), weight: (ED, 1, K), bias: (ED) or None."""
+    return _CausalConv1dSiluFn.apply(xin, weight, bias)
+
+
+# ------------------------------------------------------------------------------- decode step
+@torch.no_grad()
+def conv1d_step(xin: torch.Tensor, inputs: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]
+                ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """One token of the causal conv (mamba.py:357-358, 370).  xin: (B, ED); inputs: (B, ED, K-1).
+    Returns (u, new_inputs); ``inputs`` is not modified."""
+    dev = _require_cuda(xin, inputs, weight, bias)
+    B, ED = xin.shape
+    K = weight.shape[-1]
+    dt = xin.dtype
+    x_ = xin if xin.stride(-1) == 1 else xin.contiguous()
+    new_inputs = inputs.to(dt).contiguous().clone()
+    w_ = weight.float().reshape(ED, K).contiguous()
+    b_ = _f32(bias)
+    u = torch.empty((B, ED), dtype=dt, device=dev)
+    l = nat.lib()
+    with torch.cuda.device(dev):
+        nat.check(l.gfe_conv1d_step(_ptr(x_), x_.stride(0), _ptr(new_inputs), _ptr(w_), _ptr(b_), _ptr(u), u.stride(0),
+                                    B, ED, K, _DT[dt], _stream(dev)), "conv1d_step")
+    return u, new_inputs
+
+
+@torch.no_grad()
+def ssm_step(u, delta, A_log, Bm, Cm, D, h, z=None, dt_bias=None, delta_softplus: bool = True):
+    """One token of the selective scan (mamba.py:375-405).  u, delta, z: (B, ED); Bm, Cm: (B, N); h: (B, ED, N) or None.
+    Returns (out, h_new); ``h`` is not modified."""
+    dev = _require_cuda(u, delta, A_log, Bm, Cm, D, h, z, dt_bias)
+    B, ED = u.shape
+    N = A_log.shape[1]
+    dt = u.dtype
+
+    def row(t):
+        if t is None:
+            return None
+        t = t.to(dt)
+        return t if t.stride(-1) == 1 else t.contiguous()
+
+    u_, delta_, z_, Bm_, Cm_ = row(u), row(delta), row(z), row(Bm), row(Cm)
+    h_new = torch.zeros((B, ED, N), dtype=torch.float32, device=dev) if h is None else h.float().contiguous().clone()
+    out = torch.empty((B, ED), dtype=dt, device=dev)
+    A_log_, D_, bias_ = _f32(A_log), _f32(D), _f32(dt_bias)
+    l = nat.lib()
+    with torch.cuda.device(dev):
+        nat.check(l.gfe_ssm_step(_ptr(u_), u_.stride(0), _ptr(delta_), delta_.stride(0), _ptr(z_), 0 if z_ is None else z_.stride(0),
+                                 _ptr(Bm_), Bm_.stride(0), _ptr(Cm_), Cm_.stride(0), _ptr(A_log_), _ptr(D_), _ptr(bias_),
+                                 _ptr(h_new), _ptr(out), out.stride(0), B, ED, N,
+                                 nat.GFE_FLAG_DELTA_SOFTPLUS if delta_softplus else 0, _DT[dt], _stream(dev)), "ssm_step")
+    return out, h_new

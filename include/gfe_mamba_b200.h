@@ -1,0 +1,149 @@
+/*
+ * gfe_mamba_b200.h -- C ABI of the B200 (sm_100a) selective-scan library.
+ *
+ * This is the drop-in boundary for GFE-Mamba's Mamba hot path.  The reference
+ * (Tinysqua/GFE-Mamba) is pure Python and has no FFI of its own; the entry points
+ * below are what a binding for that path binds, one per reference function:
+ *
+ *   gfe_pscan_fwd / gfe_pscan_bwd        cross_atten/pscan.py:152-186 / :189-224  (PScan.forward / .backward)
+ *   gfe_selscan_fwd / gfe_selscan_bwd    cross_atten/mamba.py:227-286 (ssm + selective_scan, with the
+ *                                        softplus+bias of :255-256 and the silu(z) gate of :220-222 fused,
+ *                                        i.e. the contract of the selective_scan_fn call at :251)
+ *   gfe_conv1d_silu_fwd / _bwd           cross_atten/mamba.py:128-131,208-212 (causal depthwise conv + SiLU)
+ *   gfe_conv1d_step / gfe_ssm_step       cross_atten/mamba.py:357-358,370 and :375-405 (decode step)
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller; the library never
+ *     allocates, frees or retains memory, and never synchronises the stream;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - activations are channel-last (B, L, ED); strides are in ELEMENTS, the channel
+ *     (innermost) stride is always 1, so the halves of in_proj's output and the
+ *     slices of x_proj's output are consumed in place;
+ *   - parameters A_log, D, dt_bias, conv weight/bias and all parameter gradients
+ *     are fp32; `dtype` names the activation type;
+ *   - return value: GFE_OK (0) or a negative gfe_status; gfe_last_error_string()
+ *     returns a thread-local description of the last failure;
+ *   - stateless and re-entrant: safe from any host thread (e.g. autograd's).
+ */
+#ifndef GFE_MAMBA_B200_H
+#define GFE_MAMBA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define GFE_API __attribute__((visibility("default")))
+#else
+#define GFE_API
+#endif
+
+#define GFE_VERSION 100 /* 0.1.0 */
+
+enum gfe_dtype { GFE_F32 = 0, GFE_BF16 = 1, GFE_F16 = 2 };
+
+enum gfe_status {
+    GFE_OK = 0,
+    GFE_ERR_ARG = -1,         /* null pointer / non-positive size / bad flag            */
+    GFE_ERR_DTYPE = -2,       /* dtype not one of gfe_dtype                              */
+    GFE_ERR_UNSUPPORTED = -3, /* shape outside the compiled envelope (e.g. d_state != 16) */
+    GFE_ERR_WORKSPACE = -4,   /* workspace / checkpoint buffer missing or too small      */
+    GFE_ERR_CUDA = -5         /* launch failed (cudaPeekAtLastError)                      */
+};
+
+/* flags of gfe_selscan_args.flags */
+#define GFE_FLAG_DELTA_SOFTPLUS 1u /* delta = softplus(delta + dt_bias) (mamba.py:255-256); else delta + dt_bias */
+
+GFE_API int gfe_version(void);
+GFE_API const char *gfe_last_error_string(void);
+
+/* ------------------------------------------------------------------ pscan --
+ * H[t] = A[t] * H[t-1] + X[t], H[-1] = 0, independently per (b, d, n).
+ * A, X, H, dH, dA, dX: contiguous (B, L, D, N) fp32.  Any L >= 1 (the reference
+ * pads to the next power of two; results on [0, L) are identical).
+ * bwd: dX[t] = g[t] = dH[t] + A[t+1] g[t+1];  dA[t] = H[t-1] g[t], dA[0] = 0.
+ */
+GFE_API size_t gfe_pscan_workspace_bytes(int B, int L, int D, int N);
+GFE_API int gfe_pscan_fwd(const float *A, const float *X, float *H, int B, int L, int D, int N,
+                          void *ws, size_t ws_bytes, void *stream);
+GFE_API int gfe_pscan_bwd(const float *A, const float *H, const float *dH, float *dA, float *dX,
+                          int B, int L, int D, int N, void *ws, size_t ws_bytes, void *stream);
+
+/* --------------------------------------------------------- selective scan --
+ * out[b,t,c] = (sum_n C[b,t,n] h[b,t,c,n] + D[c] u[b,t,c]) * silu(z[b,t,c])
+ * h[t] = exp(delta A) h[t-1] + delta B[t] u[t],  A = -exp(A_log),
+ * delta = softplus(delta_in + dt_bias).
+ */
+typedef struct gfe_selscan_args {
+    int32_t batch, seqlen, d_inner, d_state;
+    int32_t dtype;  /* gfe_dtype of u, delta, z, Bm, Cm, out and of their gradients */
+    uint32_t flags; /* GFE_FLAG_* */
+
+    const void *u;     int64_t u_bs, u_rs;         /* (B, L, ED): batch stride, row stride */
+    const void *delta; int64_t delta_bs, delta_rs; /* (B, L, ED) pre-softplus, pre-bias    */
+    const void *z;     int64_t z_bs, z_rs;         /* (B, L, ED) or NULL (no gate)         */
+    const void *Bm;    int64_t B_bs, B_rs;         /* (B, L, N)                            */
+    const void *Cm;    int64_t C_bs, C_rs;         /* (B, L, N)                            */
+    const float *A_log;                            /* (ED, N) contiguous                   */
+    const float *D;                                /* (ED)                                 */
+    const float *dt_bias;                          /* (ED) or NULL                         */
+
+    void *out;         int64_t out_bs, out_rs;     /* (B, L, ED)   [fwd only]              */
+    float *last_state;                             /* (B, ED, N) or NULL [fwd only]        */
+
+    /* chunk checkpoints: written by fwd when non-NULL, required by bwd.
+     * gfe_selscan_ckpt_bytes() bytes, opaque layout. */
+    void *ckpt;        size_t ckpt_bytes;
+    void *ws;          size_t ws_bytes;            /* scratch, gfe_selscan_{fwd,bwd}_workspace_bytes() */
+
+    /* ---- backward only ---- */
+    const void *dout;  int64_t dout_bs, dout_rs;   /* (B, L, ED) */
+    void *du;          int64_t du_bs, du_rs;
+    void *ddelta;      int64_t ddelta_bs, ddelta_rs; /* gradient w.r.t. delta_in (pre-softplus) */
+    void *dz;          int64_t dz_bs, dz_rs;       /* NULL iff z is NULL */
+    void *dBm;         int64_t dB_bs, dB_rs;       /* (B, L, N) */
+    void *dCm;         int64_t dC_bs, dC_rs;
+    float *dA_log;                                 /* (ED, N)  overwritten */
+    float *dD;                                     /* (ED)     overwritten */
+    float *ddt_bias;                               /* (ED) or NULL, overwritten */
+} gfe_selscan_args;
+
+GFE_API size_t gfe_selscan_ckpt_bytes(int B, int L, int ED, int N);
+GFE_API size_t gfe_selscan_fwd_workspace_bytes(int B, int L, int ED, int N);
+GFE_API size_t gfe_selscan_bwd_workspace_bytes(int B, int L, int ED, int N);
+GFE_API int gfe_selscan_fwd(const gfe_selscan_args *args, void *stream);
+GFE_API int gfe_selscan_bwd(const gfe_selscan_args *args, void *stream);
+
+/* ------------------------------------------------ causal depthwise conv1d --
+ * u[b,t,c] = silu(bias[c] + sum_k w[c,k] xin[b, t-(K-1)+k, c]),  xin = 0 for t < 0.
+ * w: (ED, K) fp32 (= conv1d.weight viewed (ED,1,K)), bias: (ED) fp32 or NULL.  K <= 8.
+ */
+GFE_API int gfe_conv1d_silu_fwd(const void *xin, int64_t x_bs, int64_t x_rs, const float *w, const float *bias,
+                                void *u, int64_t u_bs, int64_t u_rs, int B, int L, int ED, int K, int dtype,
+                                void *stream);
+GFE_API size_t gfe_conv1d_bwd_workspace_bytes(int B, int L, int ED, int K);
+GFE_API int gfe_conv1d_silu_bwd(const void *xin, int64_t x_bs, int64_t x_rs, const float *w, const float *bias,
+                                const void *du, int64_t du_bs, int64_t du_rs,
+                                void *dxin, int64_t dx_bs, int64_t dx_rs, float *dw, float *dbias,
+                                int B, int L, int ED, int K, int dtype, void *ws, size_t ws_bytes, void *stream);
+
+/* ------------------------------------------------------------ decode step --
+ * gfe_conv1d_step: window = cat(inputs, xin[:, None]) (mamba.py:357); u = silu(conv(window)[K-1]);
+ *                  inputs <- window[:, :, 1:] in place (mamba.py:370).  inputs: (B, ED, K-1) activation dtype.
+ * gfe_ssm_step:    h <- exp(delta A) h + delta B u;  out = (h.C + D u) * silu(z)   (mamba.py:391-403, :364-367)
+ *                  h: (B, ED, N) fp32, updated in place; delta = softplus(delta_in + dt_bias).
+ */
+GFE_API int gfe_conv1d_step(const void *xin, int64_t x_bs, void *inputs, const float *w, const float *bias,
+                            void *u, int64_t u_bs, int B, int ED, int K, int dtype, void *stream);
+GFE_API int gfe_ssm_step(const void *u, int64_t u_bs, const void *delta, int64_t delta_bs,
+                         const void *z, int64_t z_bs, const void *Bm, int64_t B_bs, const void *Cm, int64_t C_bs,
+                         const float *A_log, const float *D, const float *dt_bias, float *h,
+                         void *out, int64_t out_bs, int B, int ED, int N, uint32_t flags, int dtype, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GFE_MAMBA_B200_H */
