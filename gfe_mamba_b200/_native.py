@@ -62,6 +62,10 @@ SIGNATURES = {
     "gfe_conv1d_step": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64] + [ctypes.c_int] * 4 + [c_vp]),
     "gfe_ssm_step": (ctypes.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp,
                                     c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_u32, ctypes.c_int, c_vp]),
+    "gfe_timing_enable": (ctypes.c_int, [ctypes.c_int]),
+    "gfe_timing_kernel_count": (ctypes.c_int, []),
+    "gfe_timing_kernel_name": (ctypes.c_char_p, [ctypes.c_int]),
+    "gfe_timing_collect": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
 }
 
 _lib = None
@@ -90,3 +94,17 @@ def check(rc: int, what: str) -> None:
     if rc != 0:
         msg = lib().gfe_last_error_string()
         raise RuntimeError(f"gfe_mamba_b200.{what} failed (status {rc}): {msg.decode() if msg else ''}")
+
+
+def timing_enable(on: bool) -> None:
+    lib().gfe_timing_enable(1 if on else 0)
+
+
+def timing_collect() -> dict:
+    """{kernel name: (total_ms, launches)} since the last collect; synchronises the recorded events."""
+    l = lib()
+    n = l.gfe_timing_kernel_count()
+    ms = (ctypes.c_double * n)()
+    cnt = (ctypes.c_int64 * n)()
+    check(l.gfe_timing_collect(ms, cnt, n), "timing_collect")
+    return {l.gfe_timing_kernel_name(i).decode(): (ms[i], cnt[i]) for i in range(n) if cnt[i] > 0}

@@ -2,6 +2,10 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <atomic>
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 namespace gfe {
@@ -65,9 +69,60 @@ SegPlan plan_segments(int B, int L, int ED) {
     return p;
 }
 
+// ---- optional per-kernel timing ------------------------------------------------------------------
+static std::atomic<int> g_timing_on{0};
+static std::mutex g_timing_mu;
+struct TimingRec { int id; cudaEvent_t a, b; };
+static std::vector<TimingRec> g_timing;
+static const char *const kKernelNames[K_COUNT] = {
+    "selscan_fwd_summary", "selscan_fwd", "selscan_bwd_summary", "selscan_bwd", "selscan_bwd_finalize_bc",
+    "selscan_bwd_finalize_par", "pscan_fwd_summary", "pscan_fwd", "pscan_bwd_summary", "pscan_bwd",
+    "conv1d_silu_fwd", "conv1d_silu_bwd", "conv1d_bwd_finalize", "conv1d_step", "ssm_step"};
+
+void timing_mark(int id, cudaStream_t st, bool begin) {
+    if (!g_timing_on.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    if (begin) {
+        TimingRec r{id, nullptr, nullptr};
+        if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) { (void)cudaGetLastError(); return; }
+        cudaEventRecord(r.a, st);
+        g_timing.push_back(r);
+    } else {
+        for (size_t i = g_timing.size(); i-- > 0;)
+            if (g_timing[i].id == id) { cudaEventRecord(g_timing[i].b, st); break; }
+    }
+}
+
 }  // namespace gfe
 
 extern "C" {
+
+GFE_API int gfe_timing_enable(int on) {
+    const int prev = gfe::g_timing_on.exchange(on ? 1 : 0);
+    return prev;
+}
+
+GFE_API int gfe_timing_kernel_count(void) { return gfe::K_COUNT; }
+
+GFE_API const char *gfe_timing_kernel_name(int id) { return (id >= 0 && id < gfe::K_COUNT) ? gfe::kKernelNames[id] : ""; }
+
+GFE_API int gfe_timing_collect(double *total_ms, int64_t *launches, int n) {
+    if (!total_ms || !launches || n < gfe::K_COUNT) { gfe::set_error("timing_collect: need arrays of %d entries", gfe::K_COUNT); return GFE_ERR_ARG; }
+    std::lock_guard<std::mutex> lk(gfe::g_timing_mu);
+    for (auto &r : gfe::g_timing) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            total_ms[r.id] += ms;
+            launches[r.id] += 1;
+        } else {
+            (void)cudaGetLastError();
+        }
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    gfe::g_timing.clear();
+    return GFE_OK;
+}
 
 GFE_API int gfe_version(void) { return GFE_VERSION; }
 

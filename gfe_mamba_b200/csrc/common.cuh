@@ -15,6 +15,19 @@ void set_error(const char *fmt, ...);
 int check_launch(const char *what);   // cudaPeekAtLastError -> GFE_OK / GFE_ERR_CUDA
 int sm_count();                       // SMs of the current device (148 on B200; 148 assumed if no device)
 
+// kernel ids of the optional timing registry (api.cu)
+enum KernelId {
+    K_SELSCAN_FWD_SUMMARY = 0, K_SELSCAN_FWD, K_SELSCAN_BWD_SUMMARY, K_SELSCAN_BWD, K_SELSCAN_BWD_FIN_BC,
+    K_SELSCAN_BWD_FIN_PAR, K_PSCAN_FWD_SUMMARY, K_PSCAN_FWD, K_PSCAN_BWD_SUMMARY, K_PSCAN_BWD,
+    K_CONV_FWD, K_CONV_BWD, K_CONV_BWD_FIN, K_CONV_STEP, K_SSM_STEP, K_COUNT
+};
+void timing_mark(int id, cudaStream_t st, bool begin);
+struct ScopedKernelTimer {   // brackets one launch with events when timing is enabled
+    int id; cudaStream_t st;
+    ScopedKernelTimer(int id_, cudaStream_t st_) : id(id_), st(st_) { timing_mark(id, st, true); }
+    ~ScopedKernelTimer() { timing_mark(id, st, false); }
+};
+
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

@@ -146,17 +146,20 @@ __global__ void __launch_bounds__(128) conv1d_bwd_finalize_kernel(ConvParams p) 
 template <typename T, int K>
 static int conv_fwd_launch(ConvParams &p, cudaStream_t st) {
     const dim3 block(128), grid((p.ED + 127) / 128, p.ntiles, p.B);
-    conv1d_silu_fwd_kernel<T, K><<<grid, block, 0, st>>>(p);
+    { ScopedKernelTimer tm(K_CONV_FWD, st);
+      conv1d_silu_fwd_kernel<T, K><<<grid, block, 0, st>>>(p); }
     return check_launch("conv1d_silu_fwd");
 }
 
 template <typename T, int K>
 static int conv_bwd_launch(ConvParams &p, cudaStream_t st) {
     const dim3 block(128), grid((p.ED + 127) / 128, p.ntiles, p.B);
-    conv1d_silu_bwd_kernel<T, K><<<grid, block, 0, st>>>(p);
+    { ScopedKernelTimer tm(K_CONV_BWD, st);
+      conv1d_silu_bwd_kernel<T, K><<<grid, block, 0, st>>>(p); }
     int rc = check_launch("conv1d_silu_bwd");
     if (rc != GFE_OK) return rc;
-    conv1d_bwd_finalize_kernel<K><<<dim3((p.ED + 127) / 128, K + 1), 128, 0, st>>>(p);
+    { ScopedKernelTimer tm(K_CONV_BWD_FIN, st);
+      conv1d_bwd_finalize_kernel<K><<<dim3((p.ED + 127) / 128, K + 1), 128, 0, st>>>(p); }
     return check_launch("conv1d_bwd_finalize");
 }
 

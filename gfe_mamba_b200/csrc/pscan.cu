@@ -204,13 +204,15 @@ GFE_API int gfe_pscan_fwd(const float *A, const float *X, float *H, int B, int L
     const int64_t nvec = v4 ? DN / 4 : DN;
     const dim3 block(128), grid((unsigned)ceil_div64(nvec, 128), pl.nseg, B);
     if (pl.nseg > 1) {
-        if (v4) pscan_fwd_kernel<4, true><<<grid, block, 0, st>>>(p);
-        else pscan_fwd_kernel<1, true><<<grid, block, 0, st>>>(p);
+        { ScopedKernelTimer tm(K_PSCAN_FWD_SUMMARY, st);
+          if (v4) pscan_fwd_kernel<4, true><<<grid, block, 0, st>>>(p);
+          else pscan_fwd_kernel<1, true><<<grid, block, 0, st>>>(p); }
         rc = check_launch("pscan_fwd_summary");
         if (rc != GFE_OK) return rc;
     }
-    if (v4) pscan_fwd_kernel<4, false><<<grid, block, 0, st>>>(p);
-    else pscan_fwd_kernel<1, false><<<grid, block, 0, st>>>(p);
+    { ScopedKernelTimer tm(K_PSCAN_FWD, st);
+      if (v4) pscan_fwd_kernel<4, false><<<grid, block, 0, st>>>(p);
+      else pscan_fwd_kernel<1, false><<<grid, block, 0, st>>>(p); }
     return check_launch("pscan_fwd");
 }
 
@@ -235,14 +237,16 @@ GFE_API int gfe_pscan_bwd(const float *A, const float *H, const float *dH, float
     const dim3 block(128);
     if (pl.nseg > 1) {
         const dim3 grid((unsigned)ceil_div64(nvec, 128), pl.nseg - 1, B);
-        if (v4) pscan_bwd_kernel<4, true><<<grid, block, 0, st>>>(p);
-        else pscan_bwd_kernel<1, true><<<grid, block, 0, st>>>(p);
+        { ScopedKernelTimer tm(K_PSCAN_BWD_SUMMARY, st);
+          if (v4) pscan_bwd_kernel<4, true><<<grid, block, 0, st>>>(p);
+          else pscan_bwd_kernel<1, true><<<grid, block, 0, st>>>(p); }
         rc = check_launch("pscan_bwd_summary");
         if (rc != GFE_OK) return rc;
     }
     const dim3 grid((unsigned)ceil_div64(nvec, 128), pl.nseg, B);
-    if (v4) pscan_bwd_kernel<4, false><<<grid, block, 0, st>>>(p);
-    else pscan_bwd_kernel<1, false><<<grid, block, 0, st>>>(p);
+    { ScopedKernelTimer tm(K_PSCAN_BWD, st);
+      if (v4) pscan_bwd_kernel<4, false><<<grid, block, 0, st>>>(p);
+      else pscan_bwd_kernel<1, false><<<grid, block, 0, st>>>(p); }
     return check_launch("pscan_bwd");
 }
 

@@ -21,6 +21,9 @@
 // 64 values), per-warp partial rows in the workspace, one small finalize kernel.  Parameter gradients
 // (dA_log, dD, ddt_bias) are accumulated per lane over its whole segment, then reduced over (b, seg)
 // by the second finalize kernel.  Everything is deterministic (no atomics).
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace gfe {
@@ -627,9 +630,39 @@ __global__ void __launch_bounds__(128) selscan_bwd_finalize_par_kernel(ScanParam
     }
 }
 
+}  // namespace gfe
+
+#include "selscan_fast.cuh"
+
+namespace gfe {
+
 // =====================================================================================================
 // Host side
 // =====================================================================================================
+
+// cp.async granularity usable for this call: 16 (all bases/strides 16-byte aligned), 4, or 0 (generic kernels).
+static int fast_path_cpb(const gfe_selscan_args *a, bool bwd) {
+    if (a->d_inner % 32 != 0) return 0;
+    const int64_t s = a->dtype == GFE_F32 ? 4 : 2;
+    const void *ptrs[6] = {a->u, a->delta, a->z, a->Bm, a->Cm, bwd ? a->dout : nullptr};
+    const int64_t strides[12] = {a->u_bs, a->u_rs, a->delta_bs, a->delta_rs, a->z ? a->z_bs : 0, a->z ? a->z_rs : 0,
+                                 a->B_bs, a->B_rs, a->C_bs, a->C_rs, bwd ? a->dout_bs : 0, bwd ? a->dout_rs : 0};
+    bool ok16 = true, ok4 = true;
+    for (const void *q : ptrs) {
+        const uintptr_t v = reinterpret_cast<uintptr_t>(q);
+        ok16 &= (v & 15) == 0;
+        ok4 &= (v & 3) == 0;
+    }
+    for (int64_t st : strides) {
+        ok16 &= (st * s) % 16 == 0;
+        ok4 &= (st * s) % 4 == 0;
+    }
+    if (const char *e = getenv("GFE_SELSCAN_PATH")) {   // debugging / A-B measurements only
+        if (!strcmp(e, "generic")) return 0;
+        if (!strcmp(e, "cp4")) ok16 = false;
+    }
+    return ok16 ? 16 : (ok4 ? 4 : 0);
+}
 
 static int warps_per_cta() { return 1; }
 
@@ -698,6 +731,12 @@ static void fill_common(ScanParams &p, const gfe_selscan_args *a, const SegPlan 
     p.G = (a->d_inner + 31) / 32;
 }
 
+template <typename K>
+static void launch_fast(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const ScanParams &p) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kernel<<<grid, block, smem, st>>>(p);
+}
+
 template <typename T>
 static int launch_fwd(const gfe_selscan_args *a, cudaStream_t st) {
     const SegPlan sp = plan_segments(a->batch, a->seqlen, a->d_inner);
@@ -717,13 +756,26 @@ static int launch_fwd(const gfe_selscan_args *a, cudaStream_t st) {
     const dim3 block(32 * W);
     const dim3 grid((p.G + W - 1) / W, sp.nseg, a->batch);
     if (sp.nseg > 1) {
-        selscan_fwd_summary_kernel<T><<<grid, block, W * kChunk * 32 * sizeof(float), st>>>(p);
+        { ScopedKernelTimer tm(K_SELSCAN_FWD_SUMMARY, st);
+          selscan_fwd_summary_kernel<T><<<grid, block, W * kChunk * 32 * sizeof(float), st>>>(p); }
         int rc = check_launch("selscan_fwd_summary");
         if (rc != GFE_OK) return rc;
     }
-    const size_t smem = (size_t)W * 2 * kChunk * 32 * sizeof(float);
-    if (a->z != nullptr) selscan_fwd_kernel<T, true><<<grid, block, smem, st>>>(p);
-    else selscan_fwd_kernel<T, false><<<grid, block, smem, st>>>(p);
+    const int cpb = fast_path_cpb(a, false);
+    if (cpb != 0) {
+        const bool hz = a->z != nullptr;
+        const size_t smem = (size_t)W * (hz ? fwd_fast_smem_per_warp<T, true>() : fwd_fast_smem_per_warp<T, false>());
+        ScopedKernelTimer tm(K_SELSCAN_FWD, st);
+        if (hz && cpb == 16) launch_fast(selscan_fwd_fast_kernel<T, true, 16>, grid, block, smem, st, p);
+        else if (hz) launch_fast(selscan_fwd_fast_kernel<T, true, 4>, grid, block, smem, st, p);
+        else if (cpb == 16) launch_fast(selscan_fwd_fast_kernel<T, false, 16>, grid, block, smem, st, p);
+        else launch_fast(selscan_fwd_fast_kernel<T, false, 4>, grid, block, smem, st, p);
+    } else {
+        const size_t smem = (size_t)W * 2 * kChunk * 32 * sizeof(float);
+        ScopedKernelTimer tm(K_SELSCAN_FWD, st);
+        if (a->z != nullptr) selscan_fwd_kernel<T, true><<<grid, block, smem, st>>>(p);
+        else selscan_fwd_kernel<T, false><<<grid, block, smem, st>>>(p);
+    }
     return check_launch("selscan_fwd");
 }
 
@@ -733,25 +785,33 @@ static int launch_bwd_z(const gfe_selscan_args *a, ScanParams &p, const SegPlan 
     const dim3 block(32 * W);
     if (sp.nseg > 1) {
         const dim3 grid((p.G + W - 1) / W, sp.nseg - 1, a->batch);
-        selscan_bwd_summary_kernel<T, HAS_Z><<<grid, block, W * kChunk * 32 * sizeof(float), st>>>(p);
+        { ScopedKernelTimer tm(K_SELSCAN_BWD_SUMMARY, st);
+          selscan_bwd_summary_kernel<T, HAS_Z><<<grid, block, W * kChunk * 32 * sizeof(float), st>>>(p); }
         int rc = check_launch("selscan_bwd_summary");
         if (rc != GFE_OK) return rc;
     }
     const dim3 grid((p.G + W - 1) / W, sp.nseg, a->batch);
-    const size_t smem = (size_t)W * kBwdSmemFloats * sizeof(float);
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(selscan_bwd_kernel<T, HAS_Z>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { set_error("selscan_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return GFE_ERR_CUDA; }
+    const int cpb = fast_path_cpb(a, true);
+    if (cpb != 0) {
+        const size_t smem = (size_t)W * bwd_fast_smem_per_warp<T, HAS_Z>();
+        ScopedKernelTimer tm(K_SELSCAN_BWD, st);
+        if (cpb == 16) launch_fast(selscan_bwd_fast_kernel<T, HAS_Z, 16>, grid, block, smem, st, p);
+        else launch_fast(selscan_bwd_fast_kernel<T, HAS_Z, 4>, grid, block, smem, st, p);
+    } else {
+        const size_t smem = (size_t)W * kBwdSmemFloats * sizeof(float);
+        ScopedKernelTimer tm(K_SELSCAN_BWD, st);
+        launch_fast(selscan_bwd_kernel<T, HAS_Z>, grid, block, smem, st, p);
     }
-    selscan_bwd_kernel<T, HAS_Z><<<grid, block, smem, st>>>(p);
     int rc = check_launch("selscan_bwd");
     if (rc != GFE_OK) return rc;
 
     const int64_t nbc = (int64_t)a->batch * a->seqlen * 32;
-    selscan_bwd_finalize_bc_kernel<T><<<(unsigned)ceil_div64(nbc, 256), 256, 0, st>>>(p);
+    { ScopedKernelTimer tm(K_SELSCAN_BWD_FIN_BC, st);
+      selscan_bwd_finalize_bc_kernel<T><<<(unsigned)ceil_div64(nbc, 256), 256, 0, st>>>(p); }
     rc = check_launch("selscan_bwd_finalize_bc");
     if (rc != GFE_OK) return rc;
-    selscan_bwd_finalize_par_kernel<<<dim3((a->d_inner + 127) / 128, 18), 128, 0, st>>>(p);
+    { ScopedKernelTimer tm(K_SELSCAN_BWD_FIN_PAR, st);
+      selscan_bwd_finalize_par_kernel<<<dim3((a->d_inner + 127) / 128, 18), 128, 0, st>>>(p); }
     return check_launch("selscan_bwd_finalize_par");
 }
 

@@ -75,6 +75,7 @@ static int conv_step_launch(const void *xin, int64_t x_bs, void *inputs, const f
     const dim3 block(128), grid((ED + 127) / 128, B);
     const T *x = reinterpret_cast<const T *>(xin);
     T *in = reinterpret_cast<T *>(inputs), *uo = reinterpret_cast<T *>(u);
+    ScopedKernelTimer tm(K_CONV_STEP, st);
     switch (K) {
         case 2: conv1d_step_kernel<T, 2><<<grid, block, 0, st>>>(x, x_bs, in, w, bias, uo, u_bs, B, ED); break;
         case 3: conv1d_step_kernel<T, 3><<<grid, block, 0, st>>>(x, x_bs, in, w, bias, uo, u_bs, B, ED); break;
@@ -90,6 +91,7 @@ static int ssm_step_launch(const void *u, int64_t u_bs, const void *delta, int64
                            const float *D, const float *dt_bias, float *h, void *out, int64_t o_bs, int B, int ED,
                            uint32_t flags, cudaStream_t st) {
     const dim3 block(128), grid((ED + 127) / 128, B);
+    ScopedKernelTimer tm(K_SSM_STEP, st);
     ssm_step_kernel<T><<<grid, block, 0, st>>>(reinterpret_cast<const T *>(u), u_bs, reinterpret_cast<const T *>(delta), d_bs,
                                                reinterpret_cast<const T *>(z), z_bs, reinterpret_cast<const T *>(Bm), B_bs,
                                                reinterpret_cast<const T *>(Cm), C_bs, A_log, D, dt_bias, h,

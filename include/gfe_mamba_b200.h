@@ -143,6 +143,17 @@ GFE_API int gfe_ssm_step(const void *u, int64_t u_bs, const void *delta, int64_t
                          const float *A_log, const float *D, const float *dt_bias, float *h,
                          void *out, int64_t out_bs, int B, int ED, int N, uint32_t flags, int dtype, void *stream);
 
+/* -------------------------------------------------------- instrumentation --
+ * Optional per-kernel device timing: when enabled, every kernel the library launches is bracketed by a
+ * cudaEvent pair on the launching stream.  gfe_timing_collect() synchronises those events, adds the elapsed
+ * milliseconds and launch counts per kernel id into the caller's arrays (length n >= gfe_timing_kernel_count())
+ * and clears the records.  Off by default (zero overhead); used by bench.py for the roofline line.
+ */
+GFE_API int gfe_timing_enable(int on);
+GFE_API int gfe_timing_kernel_count(void);
+GFE_API const char *gfe_timing_kernel_name(int id);
+GFE_API int gfe_timing_collect(double *total_ms, int64_t *launches, int n);
+
 #ifdef __cplusplus
 }
 #endif
