@@ -1,6 +1,7 @@
 // api.cu -- version / error plumbing and the host-side launch planner shared by all ops.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <mutex>
@@ -51,8 +52,17 @@ int sm_count() {
 SegPlan plan_segments(int B, int L, int ED) {
     SegPlan p;
     p.nchunks = (L + kChunk - 1) / kChunk;
-    const int64_t nwarps = (int64_t)B * ((ED + 31) / 32);
     const int64_t smsp = (int64_t)sm_count() * 4;
+    const int64_t nwarps = (int64_t)B * ((ED + 31) / 32);
+    // Two lanes per channel double the warp count of the fast kernels (needs ED % 32 == 0).  Measured on cfg3
+    // (1.3 warps per scheduler at P = 1): forward gains 30 %, backward does not (per-chunk overhead doubles),
+    // so backward only switches when it cannot even give every scheduler one warp.
+    p.p_fwd = (ED % 32 == 0 && nwarps < 2 * smsp) ? 2 : 1;
+    p.p_bwd = (ED % 32 == 0 && nwarps < smsp) ? 2 : 1;
+    if (const char *e = getenv("GFE_SELSCAN_P")) {   // A/B measurements only
+        if (e[0] == '1') p.p_fwd = p.p_bwd = 1;
+        if (e[0] == '2' && ED % 32 == 0) p.p_fwd = p.p_bwd = 2;
+    }
     int S = 1;
     if (nwarps * 2 < smsp) {
         S = (int)ceil_div64(2 * smsp, nwarps);

@@ -24,7 +24,7 @@ static PscanPlan pscan_plan(int B, int L, int64_t DN) {
     const int64_t warps = ceil_div64((int64_t)B * nvec, 32);
     const int64_t want = (int64_t)sm_count() * 16;
     int S = 1;
-    if (warps < want) {
+    if (warps * 2 < want) {   // splitting re-reads A and X once more, only worth it when the GPU is less than half full
         S = (int)ceil_div64(want, warps);
         const int max_by_len = L / 64;
         if (S > max_by_len) S = max_by_len;

@@ -39,6 +39,7 @@ struct ScanParams {
     int64_t o_bs, o_rs;
     float *last_state;
     float2 *ckpt;   // [B][nchunks][8][ED]
+    void *ysave;    // [B][L][ED] activation dtype: y before the gate (fast kernels), lives behind ckpt
     float2 *seg_h;  // [B][nseg][8][ED]  segment-local end state (fwd) / start carry (bwd)
     float *seg_sd;  // [B][nseg][ED]     sum of delta over the segment
     // backward
@@ -685,13 +686,18 @@ static WsLayout fwd_ws_layout(int B, int L, int ED, const SegPlan &sp) {
 static WsLayout bwd_ws_layout(int B, int L, int ED, const SegPlan &sp) {
     WsLayout w = fwd_ws_layout(B, L, ED, sp);
     size_t off = w.total;
-    const size_t G = (ED + 31) / 32;
+    const size_t G = (ED + 15) / 16;   // channel groups of the finest decomposition (P = 2: 16 channels per warp)
     w.part_bc = off;
     off += align_up(G * B * L * 32 * sizeof(float), 256);
     w.part_par = off;
     off += align_up((size_t)B * sp.nseg * 18 * ED * sizeof(float), 256);
     w.total = off;
     return w;
+}
+
+static size_t ckpt_state_bytes(int B, int L, int ED) {
+    const size_t nchunks = (L + kChunk - 1) / kChunk;
+    return (size_t)B * nchunks * ED * kNState * sizeof(float);
 }
 
 static int validate_common(const gfe_selscan_args *a, bool bwd) {
@@ -728,6 +734,7 @@ static void fill_common(ScanParams &p, const gfe_selscan_args *a, const SegPlan 
     p.z_bs = a->z_bs; p.z_rs = a->z_rs; p.B_bs = a->B_bs; p.B_rs = a->B_rs; p.C_bs = a->C_bs; p.C_rs = a->C_rs;
     p.A_log = a->A_log; p.D = a->D; p.dt_bias = a->dt_bias;
     p.ckpt = reinterpret_cast<float2 *>(a->ckpt);
+    p.ysave = a->ckpt ? reinterpret_cast<char *>(a->ckpt) + ckpt_state_bytes(a->batch, a->seqlen, a->d_inner) : nullptr;
     p.G = (a->d_inner + 31) / 32;
 }
 
@@ -764,12 +771,24 @@ static int launch_fwd(const gfe_selscan_args *a, cudaStream_t st) {
     const int cpb = fast_path_cpb(a, false);
     if (cpb != 0) {
         const bool hz = a->z != nullptr;
-        const size_t smem = (size_t)W * (hz ? fwd_fast_smem_per_warp<T, true>() : fwd_fast_smem_per_warp<T, false>());
+        const int P = sp.p_fwd;
+        const int Gf = a->d_inner / (32 / P);
+        const dim3 gridf((Gf + W - 1) / W, sp.nseg, a->batch);
         ScopedKernelTimer tm(K_SELSCAN_FWD, st);
-        if (hz && cpb == 16) launch_fast(selscan_fwd_fast_kernel<T, true, 16>, grid, block, smem, st, p);
-        else if (hz) launch_fast(selscan_fwd_fast_kernel<T, true, 4>, grid, block, smem, st, p);
-        else if (cpb == 16) launch_fast(selscan_fwd_fast_kernel<T, false, 16>, grid, block, smem, st, p);
-        else launch_fast(selscan_fwd_fast_kernel<T, false, 4>, grid, block, smem, st, p);
+#define GFE_FWD_FAST(HZ, CPB, PP)                                                                              \
+    launch_fast(selscan_fwd_fast_kernel<T, HZ, CPB, PP>, gridf, block, (size_t)W * fwd_fast_smem_per_warp<T, HZ, PP>(), st, p)
+        if (P == 2) {
+            if (hz && cpb == 16) GFE_FWD_FAST(true, 16, 2);
+            else if (hz) GFE_FWD_FAST(true, 4, 2);
+            else if (cpb == 16) GFE_FWD_FAST(false, 16, 2);
+            else GFE_FWD_FAST(false, 4, 2);
+        } else {
+            if (hz && cpb == 16) GFE_FWD_FAST(true, 16, 1);
+            else if (hz) GFE_FWD_FAST(true, 4, 1);
+            else if (cpb == 16) GFE_FWD_FAST(false, 16, 1);
+            else GFE_FWD_FAST(false, 4, 1);
+        }
+#undef GFE_FWD_FAST
     } else {
         const size_t smem = (size_t)W * 2 * kChunk * 32 * sizeof(float);
         ScopedKernelTimer tm(K_SELSCAN_FWD, st);
@@ -793,10 +812,19 @@ static int launch_bwd_z(const gfe_selscan_args *a, ScanParams &p, const SegPlan 
     const dim3 grid((p.G + W - 1) / W, sp.nseg, a->batch);
     const int cpb = fast_path_cpb(a, true);
     if (cpb != 0) {
-        const size_t smem = (size_t)W * bwd_fast_smem_per_warp<T, HAS_Z>();
+        const int P = sp.p_bwd;
+        p.G = a->d_inner / (32 / P);
+        const dim3 gridf((p.G + W - 1) / W, sp.nseg, a->batch);
         ScopedKernelTimer tm(K_SELSCAN_BWD, st);
-        if (cpb == 16) launch_fast(selscan_bwd_fast_kernel<T, HAS_Z, 16>, grid, block, smem, st, p);
-        else launch_fast(selscan_bwd_fast_kernel<T, HAS_Z, 4>, grid, block, smem, st, p);
+        if (P == 2) {
+            const size_t smem = (size_t)W * bwd_fast_smem_per_warp<T, HAS_Z, 2>();
+            if (cpb == 16) launch_fast(selscan_bwd_fast_kernel<T, HAS_Z, 16, 2>, gridf, block, smem, st, p);
+            else launch_fast(selscan_bwd_fast_kernel<T, HAS_Z, 4, 2>, gridf, block, smem, st, p);
+        } else {
+            const size_t smem = (size_t)W * bwd_fast_smem_per_warp<T, HAS_Z, 1>();
+            if (cpb == 16) launch_fast(selscan_bwd_fast_kernel<T, HAS_Z, 16, 1>, gridf, block, smem, st, p);
+            else launch_fast(selscan_bwd_fast_kernel<T, HAS_Z, 4, 1>, gridf, block, smem, st, p);
+        }
     } else {
         const size_t smem = (size_t)W * kBwdSmemFloats * sizeof(float);
         ScopedKernelTimer tm(K_SELSCAN_BWD, st);
@@ -847,8 +875,8 @@ extern "C" {
 
 GFE_API size_t gfe_selscan_ckpt_bytes(int B, int L, int ED, int N) {
     if (B <= 0 || L <= 0 || ED <= 0 || N != gfe::kNState) return 0;
-    const size_t nchunks = (L + gfe::kChunk - 1) / gfe::kChunk;
-    return (size_t)B * nchunks * ED * N * sizeof(float);
+    // chunk-start states (fp32) + y before the gate (up to 4 bytes per element)
+    return gfe::ckpt_state_bytes(B, L, ED) + (size_t)B * L * ED * sizeof(float);
 }
 
 GFE_API size_t gfe_selscan_fwd_workspace_bytes(int B, int L, int ED, int N) {

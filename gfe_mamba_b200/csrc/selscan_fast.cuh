@@ -16,6 +16,12 @@
 //   * forward: a configurable number of state pairs take exp2 on the FMA pipe (degree-5 polynomial,
 //     packed FFMA2) instead of MUFU.EX2, because MUFU (0.5 warp-instr/clk/SM, profiles/r01_microbench_pipes.txt)
 //     is the binding pipe of the forward recurrence.
+//   * P = 1 or 2 lanes per channel: with P = 2 a warp covers 16 channels and each lane owns 4 of the 8 state
+//     pairs, which doubles the number of warps for shapes whose B*ED/32 cannot fill the schedulers (cfg3 has
+//     1.3 warps per scheduler at P = 1).  The per-step scalar work is not duplicated: the two lanes of a
+//     channel pre-process alternate time steps and exchange the results (shared slots / shuffles).
+//   * forward saves y (pre-gate) next to the chunk checkpoints; backward reads it instead of recomputing the
+//     C contraction (HBM has slack, the issue slots do not).
 // Preconditions (checked on the host, else the generic kernels run): ED % 32 == 0; for 16-bit activations
 // even strides and 4-byte aligned bases.
 #pragma once
@@ -30,6 +36,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 template <int BYTES>
 __device__ __forceinline__ void cp_async(uint32_t dst, const void *src) {
     if constexpr (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    else if constexpr (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
     else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
@@ -110,46 +117,53 @@ __device__ __forceinline__ void softplus_group(const float (&x)[G], float (&dl)[
     }
 }
 
-constexpr int kFwdPolyPairs = 2;   // state pairs whose exp2 runs on the FMA pipe in the forward kernel
 constexpr int kGroup = 4;          // steps per rolled-loop iteration
 
-template <typename T> struct FastCfg {
-    static constexpr int kTileBytes = kChunk * 32 * (int)sizeof(T);   // one staged (16 x 32) tile
+template <typename T, int P> struct FastCfg {
+    static constexpr int kCh = 32 / P;                                 // channels per warp
+    static constexpr int kNP = kPairs / P;                             // state pairs per lane
+    static constexpr int kTileBytes = kChunk * kCh * (int)sizeof(T);   // one staged (16 x kCh) tile
+    static constexpr int kBCBytes = kChunk * 32 * (int)sizeof(T);      // staged B|C rows (16 x 32)
+    static constexpr int kFwdPoly = P == 1 ? 2 : 1;                    // pairs per lane with exp2 on the FMA pipe
 };
 
 // =====================================================================================================
 // Forward
 // =====================================================================================================
-template <typename T, bool HAS_Z>
+template <typename T, bool HAS_Z, int P>
 __host__ __device__ constexpr int fwd_fast_smem_per_warp() {
-    // 2 stages x (u, delta, [z], B|C raw) + fp32 B|C tile when T is 16-bit
-    return 2 * ((HAS_Z ? 4 : 3) * FastCfg<T>::kTileBytes) + (sizeof(T) == 4 ? 0 : kChunk * 32 * 4);
+    // 2 stages x (u, delta, [z] tiles + B|C raw rows) + fp32 B|C tile when T is 16-bit
+    return 2 * ((HAS_Z ? 3 : 2) * FastCfg<T, P>::kTileBytes + FastCfg<T, P>::kBCBytes) + (sizeof(T) == 4 ? 0 : kChunk * 32 * 4);
 }
 
-template <typename T, bool HAS_Z, int CPB>
+template <typename T, bool HAS_Z, int CPB, int P>
 __global__ void __launch_bounds__(128) selscan_fwd_fast_kernel(ScanParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int TILE = FastCfg<T>::kTileBytes;
-    constexpr int NT = HAS_Z ? 4 : 3;            // tiles per stage: u, delta, [z], bc
-    constexpr int STAGE = NT * TILE;
+    using Cfg = FastCfg<T, P>;
+    constexpr int CH = Cfg::kCh, NP = Cfg::kNP, TILE = Cfg::kTileBytes;
+    constexpr int NTILE = HAS_Z ? 3 : 2;
+    constexpr int STAGE = NTILE * TILE + Cfg::kBCBytes;
     constexpr bool CONVERT_BC = sizeof(T) != 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (g * 32 >= p.ED) return;
-    const int c = g * 32 + lane;                 // ED % 32 == 0: every lane owns a real channel
+    const int g = blockIdx.x * (blockDim.x >> 5) + warp;       // channel group of CH channels
+    if (g * CH >= p.ED) return;
+    const int cl = P == 1 ? lane : (lane >> 1);               // channel within the tile
+    const int half = P == 1 ? 0 : (lane & 1);                 // which NP pairs / which alternate steps
+    const int c = g * CH + cl;
     const int seg = blockIdx.y, b = blockIdx.z;
     const int t0 = seg * p.seg_len, t1 = min(p.L, t0 + p.seg_len);
 
-    unsigned char *sw = smem_raw + (size_t)warp * fwd_fast_smem_per_warp<T, HAS_Z>();
+    unsigned char *sw = smem_raw + (size_t)warp * fwd_fast_smem_per_warp<T, HAS_Z, P>();
     const uint32_t sw_u32 = smem_u32(sw);
     float *sBCf = CONVERT_BC ? reinterpret_cast<float *>(sw + 2 * STAGE) : nullptr;
 
-    const T *ub = reinterpret_cast<const T *>(p.u) + (int64_t)b * p.u_bs + g * 32;
-    const T *db = reinterpret_cast<const T *>(p.delta) + (int64_t)b * p.d_bs + g * 32;
-    const T *zb = HAS_Z ? reinterpret_cast<const T *>(p.z) + (int64_t)b * p.z_bs + g * 32 : nullptr;
+    const T *ub = reinterpret_cast<const T *>(p.u) + (int64_t)b * p.u_bs + g * CH;
+    const T *db = reinterpret_cast<const T *>(p.delta) + (int64_t)b * p.d_bs + g * CH;
+    const T *zb = HAS_Z ? reinterpret_cast<const T *>(p.z) + (int64_t)b * p.z_bs + g * CH : nullptr;
     const T *Bb = reinterpret_cast<const T *>(p.Bm) + (int64_t)b * p.B_bs;
     const T *Cb = reinterpret_cast<const T *>(p.Cm) + (int64_t)b * p.C_bs;
     T *ob = reinterpret_cast<T *>(p.out) + (int64_t)b * p.o_bs + c;
+    T *yb = p.ysave ? reinterpret_cast<T *>(p.ysave) + ((int64_t)b * p.L) * p.ED + c : nullptr;
     const bool sp = p.flags & GFE_FLAG_DELTA_SOFTPLUS;
     const float bias = p.dt_bias ? __ldg(p.dt_bias + c) : 0.0f;
     const float Dc = __ldg(p.D + c);
@@ -157,11 +171,11 @@ __global__ void __launch_bounds__(128) selscan_fwd_fast_kernel(ScanParams p) {
     auto issue = [&](int tb, int stage) {
         const int nrows = min(kChunk, t1 - tb);
         const uint32_t s = sw_u32 + stage * STAGE;
-        tile_issue<T, CPB, 32>(s, ub + (int64_t)tb * p.u_rs, p.u_rs, nrows, lane, 32 * sizeof(T), 0);
-        tile_issue<T, CPB, 32>(s + TILE, db + (int64_t)tb * p.d_rs, p.d_rs, nrows, lane, 32 * sizeof(T), 0);
-        if (HAS_Z) tile_issue<T, CPB, 32>(s + 2 * TILE, zb + (int64_t)tb * p.z_rs, p.z_rs, nrows, lane, 32 * sizeof(T), 0);
-        tile_issue<T, CPB, 16>(s + (NT - 1) * TILE, Bb + (int64_t)tb * p.B_rs, p.B_rs, nrows, lane, 32 * sizeof(T), 0);
-        tile_issue<T, CPB, 16>(s + (NT - 1) * TILE, Cb + (int64_t)tb * p.C_rs, p.C_rs, nrows, lane, 32 * sizeof(T), 16 * sizeof(T));
+        tile_issue<T, CPB, CH>(s, ub + (int64_t)tb * p.u_rs, p.u_rs, nrows, lane, CH * sizeof(T), 0);
+        tile_issue<T, CPB, CH>(s + TILE, db + (int64_t)tb * p.d_rs, p.d_rs, nrows, lane, CH * sizeof(T), 0);
+        if (HAS_Z) tile_issue<T, CPB, CH>(s + 2 * TILE, zb + (int64_t)tb * p.z_rs, p.z_rs, nrows, lane, CH * sizeof(T), 0);
+        tile_issue<T, CPB, 16>(s + NTILE * TILE, Bb + (int64_t)tb * p.B_rs, p.B_rs, nrows, lane, 32 * sizeof(T), 0);
+        tile_issue<T, CPB, 16>(s + NTILE * TILE, Cb + (int64_t)tb * p.C_rs, p.C_rs, nrows, lane, 32 * sizeof(T), 16 * sizeof(T));
         cp_async_commit();
     };
 
@@ -169,16 +183,25 @@ __global__ void __launch_bounds__(128) selscan_fwd_fast_kernel(ScanParams p) {
     if (t0 + kChunk < t1) issue(t0 + kChunk, 1);
     else cp_async_commit();
 
-    float2 A2[kPairs], h[kPairs];
-    load_A2(A2, p.A_log, c);
+    // this lane's NP state pairs: global pair index half * NP + q
+    float2 A2[NP], h[NP];
+    {
+        const float4 *row = reinterpret_cast<const float4 *>(p.A_log + (size_t)c * kNState + half * (2 * NP));
 #pragma unroll
-    for (int q = 0; q < kPairs; ++q) h[q] = make_float2(0.f, 0.f);
+        for (int q4 = 0; q4 < NP / 2; ++q4) {
+            const float4 v = __ldg(row + q4);
+            A2[2 * q4] = make_float2(-expf(v.x) * kLog2e, -expf(v.y) * kLog2e);
+            A2[2 * q4 + 1] = make_float2(-expf(v.z) * kLog2e, -expf(v.w) * kLog2e);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < NP; ++q) h[q] = make_float2(0.f, 0.f);
     for (int s = 0; s < seg; ++s) {   // carry-in from earlier segments
         const float sd = p.seg_sd[(size_t)(b * p.nseg + s) * p.ED + c];
-        const float2 *src = p.seg_h + ((size_t)(b * p.nseg + s) * kPairs) * p.ED + c;
+        const float2 *src = p.seg_h + ((size_t)(b * p.nseg + s) * kPairs + half * NP) * p.ED + c;
         const float2 sd2 = splat2(sd);
 #pragma unroll
-        for (int q = 0; q < kPairs; ++q) h[q] = ffma2(ex2_2(fmul2(sd2, A2[q])), h[q], src[(size_t)q * p.ED]);
+        for (int q = 0; q < NP; ++q) h[q] = ffma2(ex2_2(fmul2(sd2, A2[q])), h[q], src[(size_t)q * p.ED]);
     }
 
     int stage = 0;
@@ -191,46 +214,66 @@ __global__ void __launch_bounds__(128) selscan_fwd_fast_kernel(ScanParams p) {
         const T *sZ = reinterpret_cast<const T *>(st + 2 * TILE);
         const float *sBC;
         if (CONVERT_BC) {
-            const T *raw = reinterpret_cast<const T *>(st + (NT - 1) * TILE);
+            const T *raw = reinterpret_cast<const T *>(st + NTILE * TILE);
 #pragma unroll
             for (int j = 0; j < kChunk; ++j) sBCf[j * 32 + lane] = to_f(raw[j * 32 + lane]);
             __syncwarp();
             sBC = sBCf;
         } else {
-            sBC = reinterpret_cast<const float *>(st + (NT - 1) * TILE);
+            sBC = reinterpret_cast<const float *>(st + NTILE * TILE);
         }
+        sBC += half * (2 * NP);   // this lane's states inside the B (and, +16, C) row
 
         if (p.ckpt != nullptr) {   // state at the start of this chunk, for backward
-            float2 *dst = p.ckpt + ((size_t)(b * p.nchunks + tb / kChunk) * kPairs) * p.ED + c;
+            float2 *dst = p.ckpt + ((size_t)(b * p.nchunks + tb / kChunk) * kPairs + half * NP) * p.ED + c;
 #pragma unroll
-            for (int q = 0; q < kPairs; ++q) __stcs(dst + (size_t)q * p.ED, h[q]);
+            for (int q = 0; q < NP; ++q) __stcs(dst + (size_t)q * p.ED, h[q]);
         }
 
 #pragma unroll 1
         for (int j0 = 0; j0 < kChunk; j0 += kGroup) {
-            float x[kGroup], uj[kGroup], dl[kGroup], gate[kGroup], sgdummy[kGroup];
+            // ---- per-step scalars: with P = 2 the two lanes of a channel take alternate steps and swap results
+            constexpr int GP = kGroup / P;
+            float xo[GP], dlo[GP], uo[GP], gate[GP], sgd[GP];
 #pragma unroll
-            for (int i = 0; i < kGroup; ++i) {
-                const int j = j0 + i;
-                x[i] = to_f(sD[j * 32 + lane]) + bias;
-                uj[i] = to_f(sU[j * 32 + lane]);
+            for (int i = 0; i < GP; ++i) {
+                const int j = j0 + i * P + half;
+                xo[i] = to_f(sD[j * CH + cl]) + bias;
+                uo[i] = to_f(sU[j * CH + cl]);
                 if (HAS_Z) {
-                    const float zj = to_f(sZ[j * 32 + lane]);
+                    const float zj = to_f(sZ[j * CH + cl]);
                     gate[i] = zj * sigmoid_fast(zj);
                 }
             }
             if (sp) {
-                softplus_group<kGroup, false>(x, dl, sgdummy);
+                softplus_group<GP, false>(xo, dlo, sgd);
             } else {
 #pragma unroll
-                for (int i = 0; i < kGroup; ++i) dl[i] = x[i];
+                for (int i = 0; i < GP; ++i) dlo[i] = xo[i];
             }
 #pragma unroll
-            for (int i = 0; i < kGroup; ++i) {
-                const bool valid = tb + j0 + i < t1;   // warp-uniform
-                dl[i] = valid ? dl[i] : 0.f;
-                uj[i] = valid ? uj[i] : 0.f;
+            for (int i = 0; i < GP; ++i) {
+                const bool valid = tb + j0 + i * P + half < t1;
+                dlo[i] = valid ? dlo[i] : 0.f;     // padded step: a = 1, bx = 0 -> state untouched
+                uo[i] = valid ? uo[i] : 0.f;
             }
+            float dl[kGroup], uj[kGroup];
+            if (P == 1) {
+#pragma unroll
+                for (int i = 0; i < kGroup; ++i) { dl[i] = dlo[i / P]; uj[i] = uo[i / P]; }
+            } else {
+#pragma unroll
+                for (int i = 0; i < GP; ++i) {
+                    const float dlx = __shfl_xor_sync(0xffffffffu, dlo[i], 1);
+                    const float ux = __shfl_xor_sync(0xffffffffu, uo[i], 1);
+                    dl[2 * i] = half ? dlx : dlo[i];
+                    dl[2 * i + 1] = half ? dlo[i] : dlx;
+                    uj[2 * i] = half ? ux : uo[i];
+                    uj[2 * i + 1] = half ? uo[i] : ux;
+                }
+            }
+            // ---- recurrences of this lane's NP state pairs over the 4 steps
+            float ys[kGroup];
 #pragma unroll
             for (int i = 0; i < kGroup; ++i) {
                 const int j = j0 + i;
@@ -238,19 +281,29 @@ __global__ void __launch_bounds__(128) selscan_fwd_fast_kernel(ScanParams p) {
                 float2 y2 = make_float2(0.f, 0.f);
                 const float4 *sb = reinterpret_cast<const float4 *>(sBC + j * 32);
 #pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
+                for (int q4 = 0; q4 < NP / 2; ++q4) {
                     const float4 Bq = sb[q4], Cq = sb[4 + q4];
                     const float2 x0 = fmul2(dl2, A2[2 * q4]), x1 = fmul2(dl2, A2[2 * q4 + 1]);
-                    const float2 a0 = (2 * q4 < kFwdPolyPairs) ? ex2_poly2(x0) : ex2_2(x0);
-                    const float2 a1 = (2 * q4 + 1 < kFwdPolyPairs) ? ex2_poly2(x1) : ex2_2(x1);
+                    const float2 a0 = (2 * q4 < Cfg::kFwdPoly) ? ex2_poly2(x0) : ex2_2(x0);
+                    const float2 a1 = (2 * q4 + 1 < Cfg::kFwdPoly) ? ex2_poly2(x1) : ex2_2(x1);
                     h[2 * q4] = ffma2(a0, h[2 * q4], fmul2(du2, make_float2(Bq.x, Bq.y)));
                     y2 = ffma2(h[2 * q4], make_float2(Cq.x, Cq.y), y2);
                     h[2 * q4 + 1] = ffma2(a1, h[2 * q4 + 1], fmul2(du2, make_float2(Bq.z, Bq.w)));
                     y2 = ffma2(h[2 * q4 + 1], make_float2(Cq.z, Cq.w), y2);
                 }
-                float y = fmaf(Dc, uj[i], y2.x + y2.y);
-                if (HAS_Z) y *= gate[i];
-                if (tb + j < t1) st_stream(ob + (int64_t)(tb + j) * p.o_rs, from_f<T>(y));
+                ys[i] = y2.x + y2.y;
+                if (P == 2) ys[i] += __shfl_xor_sync(0xffffffffu, ys[i], 1);
+            }
+            // ---- D skip, gate, stores: each lane finishes the steps it pre-processed
+#pragma unroll
+            for (int i = 0; i < GP; ++i) {
+                const int j = j0 + i * P + half;
+                float y = fmaf(Dc, uo[i], P == 1 ? ys[i] : (half ? ys[2 * i + 1] : ys[2 * i]));
+                if (tb + j < t1) {
+                    if (yb != nullptr) st_stream(yb + (int64_t)(tb + j) * p.ED, from_f<T>(y));
+                    if (HAS_Z) y *= gate[i];
+                    st_stream(ob + (int64_t)(tb + j) * p.o_rs, from_f<T>(y));
+                }
             }
         }
         __syncwarp();   // every lane is done with this stage before it is refilled
@@ -259,55 +312,62 @@ __global__ void __launch_bounds__(128) selscan_fwd_fast_kernel(ScanParams p) {
     }
 
     if (p.last_state != nullptr && seg == p.nseg - 1) {
-        float2 *dst = reinterpret_cast<float2 *>(p.last_state + ((size_t)b * p.ED + c) * kNState);
+        float2 *dst = reinterpret_cast<float2 *>(p.last_state + ((size_t)b * p.ED + c) * kNState) + half * NP;
 #pragma unroll
-        for (int q = 0; q < kPairs; ++q) dst[q] = h[q];
+        for (int q = 0; q < NP; ++q) dst[q] = h[q];
     }
 }
 
 // =====================================================================================================
 // Backward
 // =====================================================================================================
-template <typename T, bool HAS_Z>
+template <typename T, bool HAS_Z, int P>
 __host__ __device__ constexpr int bwd_fast_smem_per_warp() {
-    // 2 stages x (u, delta, dout, [z], B|C raw) + fp32 B|C tile (16-bit only) + reduced tile
-    // + 4 per-(pair, lane) float2 arrays (A, G, dA, H) + 2 per-(step, lane) float arrays (f, sigmoid)
-    return 2 * ((HAS_Z ? 5 : 4) * FastCfg<T>::kTileBytes) + (sizeof(T) == 4 ? 0 : kChunk * 32 * 4) +
-           kChunk * kRedStride * 4 + 4 * (kPairs * 32 * 8) + 2 * (kChunk * 32 * 4);
+    // 2 stages x (u, delta, dout, y, [z] tiles + B|C raw rows) + fp32 B|C tile (16-bit only) + reduced dB|dC tile
+    // + 5 per-(pair, lane) float2 arrays (A, G, dA, H x 2 stages) + 5 per-(step, lane) float arrays (dl, dlu, dy, f, sigmoid)
+    return 2 * ((HAS_Z ? 5 : 4) * FastCfg<T, P>::kTileBytes + FastCfg<T, P>::kBCBytes) + (sizeof(T) == 4 ? 0 : kChunk * 32 * 4) +
+           kChunk * kRedStride * 4 + 5 * (FastCfg<T, P>::kNP * 32 * 8) + 5 * (kChunk * 32 * 4);
 }
 
-template <typename T, bool HAS_Z, int CPB>
+template <typename T, bool HAS_Z, int CPB, int P>
 __global__ void __launch_bounds__(128) selscan_bwd_fast_kernel(ScanParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int TILE = FastCfg<T>::kTileBytes;
-    constexpr int NT = HAS_Z ? 5 : 4;            // tiles per stage: u, delta, dout, [z], bc
-    constexpr int STAGE = NT * TILE;
+    using Cfg = FastCfg<T, P>;
+    constexpr int CH = Cfg::kCh, NP = Cfg::kNP, TILE = Cfg::kTileBytes;
+    constexpr int NTILE = HAS_Z ? 5 : 4;         // u, delta, dout, y, [z]
+    constexpr int STAGE = NTILE * TILE + Cfg::kBCBytes;
     constexpr bool CONVERT_BC = sizeof(T) != 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (g * 32 >= p.ED) return;
-    const int c = g * 32 + lane;
+    if (g * CH >= p.ED) return;
+    const int cl = P == 1 ? lane : (lane >> 1);
+    const int half = P == 1 ? 0 : (lane & 1);
+    const int c = g * CH + cl;
     const int seg = blockIdx.y, b = blockIdx.z;
     const int t0 = seg * p.seg_len, t1 = min(p.L, t0 + p.seg_len);
 
-    unsigned char *sw = smem_raw + (size_t)warp * bwd_fast_smem_per_warp<T, HAS_Z>();
+    unsigned char *sw = smem_raw + (size_t)warp * bwd_fast_smem_per_warp<T, HAS_Z, P>();
     const uint32_t sw_u32 = smem_u32(sw);
     unsigned char *cur = sw + 2 * STAGE;
     float *sBCf = reinterpret_cast<float *>(cur);
     if (CONVERT_BC) cur += kChunk * 32 * 4;
     float *sRed = reinterpret_cast<float *>(cur);
     cur += kChunk * kRedStride * 4;
-    float2 *sA = reinterpret_cast<float2 *>(cur);
-    float2 *sG = sA + kPairs * 32;
-    float2 *sdA = sG + kPairs * 32;
-    float2 *sH = sdA + kPairs * 32;
-    float *sF = reinterpret_cast<float *>(sH + kPairs * 32);
+    float2 *sA = reinterpret_cast<float2 *>(cur);   // natural A = -exp(A_log), this lane's pairs
+    float2 *sG = sA + NP * 32;                      // reverse carry a[t+1] g[t+1]
+    float2 *sdA = sG + NP * 32;                     // dA accumulators
+    float2 *sH = sdA + NP * 32;                     // checkpointed state at the chunk start, one copy per stage
+    float *sDl = reinterpret_cast<float *>(sH + 2 * NP * 32);
+    float *sDlu = sDl + kChunk * 32;
+    float *sDy = sDlu + kChunk * 32;
+    float *sF = sDy + kChunk * 32;
     float *sSg = sF + kChunk * 32;
 
-    const T *ub = reinterpret_cast<const T *>(p.u) + (int64_t)b * p.u_bs + g * 32;
-    const T *db = reinterpret_cast<const T *>(p.delta) + (int64_t)b * p.d_bs + g * 32;
-    const T *gb = reinterpret_cast<const T *>(p.dout) + (int64_t)b * p.do_bs + g * 32;
-    const T *zb = HAS_Z ? reinterpret_cast<const T *>(p.z) + (int64_t)b * p.z_bs + g * 32 : nullptr;
+    const T *ub = reinterpret_cast<const T *>(p.u) + (int64_t)b * p.u_bs + g * CH;
+    const T *db = reinterpret_cast<const T *>(p.delta) + (int64_t)b * p.d_bs + g * CH;
+    const T *gb = reinterpret_cast<const T *>(p.dout) + (int64_t)b * p.do_bs + g * CH;
+    const T *yb = reinterpret_cast<const T *>(p.ysave) + ((int64_t)b * p.L) * p.ED + g * CH;
+    const T *zb = HAS_Z ? reinterpret_cast<const T *>(p.z) + (int64_t)b * p.z_bs + g * CH : nullptr;
     const T *Bb = reinterpret_cast<const T *>(p.Bm) + (int64_t)b * p.B_bs;
     const T *Cb = reinterpret_cast<const T *>(p.Cm) + (int64_t)b * p.C_bs;
     T *dub = reinterpret_cast<T *>(p.du) + (int64_t)b * p.du_bs + c;
@@ -323,126 +383,135 @@ __global__ void __launch_bounds__(128) selscan_bwd_fast_kernel(ScanParams p) {
         const int tb = k * kChunk;
         const int nrows = min(kChunk, t1 - tb);
         const uint32_t s = sw_u32 + stage * STAGE;
-        tile_issue<T, CPB, 32>(s, ub + (int64_t)tb * p.u_rs, p.u_rs, nrows, lane, 32 * sizeof(T), 0);
-        tile_issue<T, CPB, 32>(s + TILE, db + (int64_t)tb * p.d_rs, p.d_rs, nrows, lane, 32 * sizeof(T), 0);
-        tile_issue<T, CPB, 32>(s + 2 * TILE, gb + (int64_t)tb * p.do_rs, p.do_rs, nrows, lane, 32 * sizeof(T), 0);
-        if (HAS_Z) tile_issue<T, CPB, 32>(s + 3 * TILE, zb + (int64_t)tb * p.z_rs, p.z_rs, nrows, lane, 32 * sizeof(T), 0);
-        tile_issue<T, CPB, 16>(s + (NT - 1) * TILE, Bb + (int64_t)tb * p.B_rs, p.B_rs, nrows, lane, 32 * sizeof(T), 0);
-        tile_issue<T, CPB, 16>(s + (NT - 1) * TILE, Cb + (int64_t)tb * p.C_rs, p.C_rs, nrows, lane, 32 * sizeof(T), 16 * sizeof(T));
+        tile_issue<T, CPB, CH>(s, ub + (int64_t)tb * p.u_rs, p.u_rs, nrows, lane, CH * sizeof(T), 0);
+        tile_issue<T, CPB, CH>(s + TILE, db + (int64_t)tb * p.d_rs, p.d_rs, nrows, lane, CH * sizeof(T), 0);
+        tile_issue<T, CPB, CH>(s + 2 * TILE, gb + (int64_t)tb * p.do_rs, p.do_rs, nrows, lane, CH * sizeof(T), 0);
+        if (HAS_Z) {   // y is only needed for dz
+            tile_issue<T, CPB, CH>(s + 3 * TILE, yb + (int64_t)tb * p.ED, p.ED, nrows, lane, CH * sizeof(T), 0);
+            tile_issue<T, CPB, CH>(s + 4 * TILE, zb + (int64_t)tb * p.z_rs, p.z_rs, nrows, lane, CH * sizeof(T), 0);
+        }
+        tile_issue<T, CPB, 16>(s + NTILE * TILE, Bb + (int64_t)tb * p.B_rs, p.B_rs, nrows, lane, 32 * sizeof(T), 0);
+        tile_issue<T, CPB, 16>(s + NTILE * TILE, Cb + (int64_t)tb * p.C_rs, p.C_rs, nrows, lane, 32 * sizeof(T), 16 * sizeof(T));
+        {   // this lane's chunk-start states (written by the forward pass)
+            const float2 *ck = p.ckpt + ((size_t)(b * p.nchunks + k) * kPairs + half * NP) * p.ED + c;
+#pragma unroll
+            for (int q = 0; q < NP; ++q) cp_async<8>(smem_u32(sH + (stage * NP + q) * 32 + lane), ck + (size_t)q * p.ED);
+        }
         cp_async_commit();
     };
     issue(last_chunk, 0);
     if (last_chunk - 1 >= first_chunk) issue(last_chunk - 1, 1);
     else cp_async_commit();
 
-    {   // per-lane constants and carries
-        const float4 *row = reinterpret_cast<const float4 *>(p.A_log + (size_t)c * kNState);
+    {   // per-lane constants and carries (this lane's NP pairs: global pair index half * NP + q)
+        const float4 *row = reinterpret_cast<const float4 *>(p.A_log + (size_t)c * kNState + half * (2 * NP));
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 v = __ldg(row + q);
-            sA[(2 * q) * 32 + lane] = make_float2(-expf(v.x), -expf(v.y));
-            sA[(2 * q + 1) * 32 + lane] = make_float2(-expf(v.z), -expf(v.w));
+        for (int q4 = 0; q4 < NP / 2; ++q4) {
+            const float4 v = __ldg(row + q4);
+            sA[(2 * q4) * 32 + lane] = make_float2(-expf(v.x), -expf(v.y));
+            sA[(2 * q4 + 1) * 32 + lane] = make_float2(-expf(v.z), -expf(v.w));
         }
 #pragma unroll
-        for (int q = 0; q < kPairs; ++q) {
+        for (int q = 0; q < NP; ++q) {
             sG[q * 32 + lane] = make_float2(0.f, 0.f);
             sdA[q * 32 + lane] = make_float2(0.f, 0.f);
         }
         for (int s = p.nseg - 1; s > seg; --s) {
             const float sd = p.seg_sd[(size_t)(b * p.nseg + s) * p.ED + c];
-            const float2 *src = p.seg_h + ((size_t)(b * p.nseg + s) * kPairs) * p.ED + c;
+            const float2 *src = p.seg_h + ((size_t)(b * p.nseg + s) * kPairs + half * NP) * p.ED + c;
             const float2 sd2 = splat2(sd * kLog2e);
 #pragma unroll
-            for (int q = 0; q < kPairs; ++q)
+            for (int q = 0; q < NP; ++q)
                 sG[q * 32 + lane] = ffma2(ex2_2(fmul2(sd2, sA[q * 32 + lane])), sG[q * 32 + lane], src[(size_t)q * p.ED]);
         }
     }
     float dD_acc = 0.f, dbias_acc = 0.f;
+    // shared-slot column of the lane that pre-processes even / odd steps of this lane's channel
+    const int col_e = P == 1 ? lane : (lane & ~1), col_o = P == 1 ? lane : (lane | 1);
 
     int stage = 0;
     for (int k = last_chunk; k >= first_chunk; --k, stage ^= 1) {
         const int tb = k * kChunk;
-        {   // this chunk's checkpoint: issue the loads before waiting on the tile
-            const float2 *ck = p.ckpt + ((size_t)(b * p.nchunks + k) * kPairs) * p.ED + c;
-            float2 hk[kPairs];
-#pragma unroll
-            for (int q = 0; q < kPairs; ++q) hk[q] = __ldcs(ck + (size_t)q * p.ED);
-            cp_async_wait<1>();
-            __syncwarp();
-#pragma unroll
-            for (int q = 0; q < kPairs; ++q) sH[q * 32 + lane] = hk[q];
-        }
+        cp_async_wait<1>();
+        __syncwarp();
         const unsigned char *st = sw + stage * STAGE;
         const T *sU = reinterpret_cast<const T *>(st);
         const T *sD = reinterpret_cast<const T *>(st + TILE);
         const T *sDo = reinterpret_cast<const T *>(st + 2 * TILE);
-        const T *sZ = reinterpret_cast<const T *>(st + 3 * TILE);
+        const T *sY = reinterpret_cast<const T *>(st + 3 * TILE);
+        const T *sZ = reinterpret_cast<const T *>(st + 4 * TILE);
         const float *sBC;
         if (CONVERT_BC) {
-            const T *raw = reinterpret_cast<const T *>(st + (NT - 1) * TILE);
+            const T *raw = reinterpret_cast<const T *>(st + NTILE * TILE);
 #pragma unroll
             for (int j = 0; j < kChunk; ++j) sBCf[j * 32 + lane] = to_f(raw[j * 32 + lane]);
             sBC = sBCf;
         } else {
-            sBC = reinterpret_cast<const float *>(st + (NT - 1) * TILE);
+            sBC = reinterpret_cast<const float *>(st + NTILE * TILE);
         }
+        sBC += half * (2 * NP);
 
-        // ---- per-step scalars of this lane's channel ----
-        float dl[kChunk], dlu[kChunk], dy[kChunk];
+        // ---- per-step scalars: each lane pre-processes kChunk / P steps (alternate steps when P = 2) ----
+        constexpr int GP = kGroup / P;
 #pragma unroll
         for (int j0 = 0; j0 < kChunk; j0 += kGroup) {
-            float x[kGroup], dlg[kGroup], sg[kGroup];
+            float x[GP], dlg[GP], sg[GP];
 #pragma unroll
-            for (int i = 0; i < kGroup; ++i) x[i] = to_f(sD[(j0 + i) * 32 + lane]) + bias;
+            for (int i = 0; i < GP; ++i) x[i] = to_f(sD[(j0 + i * P + half) * CH + cl]) + bias;
             if (sp) {
-                softplus_group<kGroup, true>(x, dlg, sg);
+                softplus_group<GP, true>(x, dlg, sg);
             } else {
 #pragma unroll
-                for (int i = 0; i < kGroup; ++i) { dlg[i] = x[i]; sg[i] = 1.0f; }
+                for (int i = 0; i < GP; ++i) { dlg[i] = x[i]; sg[i] = 1.0f; }
             }
 #pragma unroll
-            for (int i = 0; i < kGroup; ++i) {
-                const int j = j0 + i;
+            for (int i = 0; i < GP; ++i) {
+                const int j = j0 + i * P + half;
                 const bool valid = tb + j < t1;
-                const float uj = valid ? to_f(sU[j * 32 + lane]) : 0.f;
-                const float doj = valid ? to_f(sDo[j * 32 + lane]) : 0.f;
-                dl[j] = valid ? dlg[i] : 0.f;
-                dlu[j] = dl[j] * uj;
-                float f = 0.f;
+                const float uj = valid ? to_f(sU[j * CH + cl]) : 0.f;
+                const float doj = valid ? to_f(sDo[j * CH + cl]) : 0.f;
+                const float dlj = valid ? dlg[i] : 0.f;
+                float f = 0.f, dyj = doj;
                 if (HAS_Z) {
-                    const float zj = to_f(sZ[j * 32 + lane]);
+                    const float zj = to_f(sZ[j * CH + cl]);
                     const float sz = sigmoid_fast(zj);
-                    dy[j] = doj * (zj * sz);
-                    f = doj * sz * fmaf(zj, 1.0f - sz, 1.0f);
-                } else {
-                    dy[j] = doj;
+                    dyj = doj * (zj * sz);
+                    f = doj * sz * fmaf(zj, 1.0f - sz, 1.0f);   // dout * d silu(z)/dz ; dz = f * y
                 }
+                sDl[j * 32 + lane] = dlj;
+                sDlu[j * 32 + lane] = dlj * uj;
+                sDy[j * 32 + lane] = dyj;
                 sF[j * 32 + lane] = f;
                 sSg[j * 32 + lane] = sg[i];
             }
         }
-        __syncwarp();   // converted B|C tile visible to all lanes
-
-        float S1[kChunk], S2[kChunk], yv[kChunk];
+        __syncwarp();   // converted B|C tile and the per-step slots are visible to all lanes
+        float dl[kChunk], dlu[kChunk], dy[kChunk];
 #pragma unroll
-        for (int j = 0; j < kChunk; ++j) S1[j] = S2[j] = yv[j] = 0.f;
+        for (int j = 0; j < kChunk; ++j) {
+            const int col = (P == 1 || (j & 1) == 0) ? col_e : col_o;
+            dl[j] = sDl[j * 32 + col];
+            dlu[j] = sDlu[j * 32 + col];
+            dy[j] = sDy[j * 32 + col];
+        }
+
+        float2 S1[kChunk], S2[kChunk];   // packed partial sums over the pair's two states
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j) S1[j] = S2[j] = make_float2(0.f, 0.f);
 
         // ---- one state pair at a time: forward sweep (recompute), reverse sweep (gradients) ----
 #pragma unroll 1
-        for (int q = 0; q < kPairs; ++q) {
+        for (int q = 0; q < NP; ++q) {
             const float2 Aq = sA[q * 32 + lane];
             const float2 A2q = fmul2(Aq, splat2(kLog2e));
             const float *bq = sBC + 2 * q;
-            float2 h = sH[q * 32 + lane];
-            float2 a[kChunk], hp[kChunk];
+            float2 a[kChunk], hs[kChunk + 1];   // hs[j] = state before step j, hs[j+1] = state after it
+            hs[0] = sH[(stage * NP + q) * 32 + lane];
 #pragma unroll
             for (int j = 0; j < kChunk; ++j) {
                 const float2 Bq = *reinterpret_cast<const float2 *>(bq + j * 32);
-                const float2 Cq = *reinterpret_cast<const float2 *>(bq + j * 32 + 16);
                 a[j] = ex2_2(fmul2(splat2(dl[j]), A2q));
-                hp[j] = h;
-                h = ffma2(a[j], h, fmul2(splat2(dlu[j]), Bq));
-                yv[j] = fmaf(h.x, Cq.x, fmaf(h.y, Cq.y, yv[j]));
+                hs[j + 1] = ffma2(a[j], hs[j], fmul2(splat2(dlu[j]), Bq));
             }
             float2 G = sG[q * 32 + lane];
             float2 dA = sdA[q * 32 + lane];
@@ -451,29 +520,39 @@ __global__ void __launch_bounds__(128) selscan_bwd_fast_kernel(ScanParams p) {
             for (int j = kChunk - 1; j >= 0; --j) {
                 const float2 Bq = *reinterpret_cast<const float2 *>(bq + j * 32);
                 const float2 Cq = *reinterpret_cast<const float2 *>(bq + j * 32 + 16);
-                const float2 gg = ffma2(Cq, splat2(dy[j]), G);
-                const float2 dc = fmul2(splat2(dy[j]), h);
-                const float2 dbv = fmul2(gg, splat2(dlu[j]));
+                const float2 gg = ffma2(Cq, splat2(dy[j]), G);          // g[t] = C dy + a[t+1] g[t+1]
+                const float2 dc = fmul2(splat2(dy[j]), hs[j + 1]);      // dC_t[n] += dy * h[t]
+                const float2 dbv = fmul2(gg, splat2(dlu[j]));           // dB_t[n] += g * delta * u
                 v[2 * j] = dbv.x;
                 v[2 * j + 1] = dbv.y;
                 v[32 + 2 * j] = dc.x;
                 v[32 + 2 * j + 1] = dc.y;
-                S1[j] = fmaf(gg.x, Bq.x, fmaf(gg.y, Bq.y, S1[j]));
-                G = fmul2(a[j], gg);
-                const float2 t1v = fmul2(G, hp[j]);
-                S2[j] = fmaf(t1v.x, Aq.x, fmaf(t1v.y, Aq.y, S2[j]));
-                dA = ffma2(t1v, splat2(dl[j]), dA);
-                h = hp[j];
+                S1[j] = ffma2(gg, Bq, S1[j]);                           // sum_n g B
+                G = fmul2(a[j], gg);                                    // a[t] g[t]
+                const float2 t1v = fmul2(G, hs[j]);                     // g a h[t-1]  (= d a * a)
+                S2[j] = ffma2(t1v, Aq, S2[j]);                          // sum_n (da a) A
+                dA = ffma2(t1v, splat2(dl[j]), dA);                     // dA[c,n] += (da a) delta
             }
             sG[q * 32 + lane] = G;
             sdA[q * 32 + lane] = dA;
 
+            const int qg = half * NP + q;   // global pair index
             transpose_reduce_step<32>(v, lane);
             transpose_reduce_step<16>(v, lane);
             transpose_reduce_step<8>(v, lane);
             transpose_reduce_step<4>(v, lane);
-            transpose_reduce_step<2>(v, lane);
-            *reinterpret_cast<float2 *>(sRed + (lane & 15) * kRedStride + (lane >> 4) * 16 + 2 * q) = make_float2(v[0], v[1]);
+            if (P == 1) {
+                transpose_reduce_step<2>(v, lane);
+                // lane l owns values 2l, 2l+1: kind = l >> 4 (0: dB, 1: dC), step = l & 15, states 2q, 2q+1
+                *reinterpret_cast<float2 *>(sRed + (lane & 15) * kRedStride + (lane >> 4) * 16 + 2 * qg) = make_float2(v[0], v[1]);
+            } else {
+                // reduced over the 16 lanes of equal parity; lane owns values 4L'..4L'+3, L' = lane >> 1:
+                // kind = L' >> 3, steps 2 (L' & 7) and 2 (L' & 7) + 1
+                const int Lp = lane >> 1, jj = 2 * (Lp & 7);
+                float *dst = sRed + jj * kRedStride + (Lp >> 3) * 16 + 2 * qg;
+                *reinterpret_cast<float2 *>(dst) = make_float2(v[0], v[1]);
+                *reinterpret_cast<float2 *>(dst + kRedStride) = make_float2(v[2], v[3]);
+            }
         }
         __syncwarp();
 
@@ -485,21 +564,40 @@ __global__ void __launch_bounds__(128) selscan_bwd_fast_kernel(ScanParams p) {
                 if (tb + j < t1) __stcs(dst + (size_t)j * 32, sRed[j * kRedStride + lane]);
         }
 
-        // ---- per-(t, c) outputs ----
+        // ---- per-(t, c) outputs: each lane finishes the steps it pre-processed (no divergence) ----
 #pragma unroll
-        for (int j = 0; j < kChunk; ++j) {
+        for (int i = 0; i < kChunk / P; ++i) {
+            float s1, s2, dlj, dyj;
+            if (P == 1) {
+                s1 = S1[i].x + S1[i].y;
+                s2 = S2[i].x + S2[i].y;
+                dlj = dl[i];
+                dyj = dy[i];
+            } else {   // totals over both lanes of the channel for steps 2i and 2i+1, then keep the own one
+                float s1e = S1[2 * i].x + S1[2 * i].y, s1o = S1[2 * i + 1].x + S1[2 * i + 1].y;
+                float s2e = S2[2 * i].x + S2[2 * i].y, s2o = S2[2 * i + 1].x + S2[2 * i + 1].y;
+                s1e += __shfl_xor_sync(0xffffffffu, s1e, 1);
+                s1o += __shfl_xor_sync(0xffffffffu, s1o, 1);
+                s2e += __shfl_xor_sync(0xffffffffu, s2e, 1);
+                s2o += __shfl_xor_sync(0xffffffffu, s2o, 1);
+                s1 = half ? s1o : s1e;
+                s2 = half ? s2o : s2e;
+                dlj = half ? dl[2 * i + 1] : dl[2 * i];
+                dyj = half ? dy[2 * i + 1] : dy[2 * i];
+            }
+            const int j = i * P + half;
             if (tb + j < t1) {
-                const float uj = to_f(sU[j * 32 + lane]);
-                const float ddl = fmaf(S1[j], uj, S2[j]);
-                const float draw = ddl * sSg[j * 32 + lane];
-                st_stream(dub + (int64_t)(tb + j) * p.du_rs, from_f<T>(fmaf(dl[j], S1[j], Dc * dy[j])));
+                const float uj = to_f(sU[j * CH + cl]);
+                const float ddl = fmaf(s1, uj, s2);                     // d delta
+                const float draw = ddl * sSg[j * 32 + lane];            // through softplus
+                st_stream(dub + (int64_t)(tb + j) * p.du_rs, from_f<T>(fmaf(dlj, s1, Dc * dyj)));
                 st_stream(ddb + (int64_t)(tb + j) * p.dd_rs, from_f<T>(draw));
-                if (HAS_Z) st_stream(dzb + (int64_t)(tb + j) * p.dz_rs, from_f<T>(sF[j * 32 + lane] * fmaf(Dc, uj, yv[j])));
-                dD_acc = fmaf(dy[j], uj, dD_acc);
+                if (HAS_Z) st_stream(dzb + (int64_t)(tb + j) * p.dz_rs, from_f<T>(sF[j * 32 + lane] * to_f(sY[j * CH + cl])));
+                dD_acc = fmaf(dyj, uj, dD_acc);
                 dbias_acc += draw;
             }
         }
-        __syncwarp();   // stage, sBCf and sRed are free again
+        __syncwarp();   // stage, sBCf, sRed and the slots are free again
         if (k - 2 >= first_chunk) issue(k - 2, stage);
         else cp_async_commit();
     }
@@ -507,13 +605,19 @@ __global__ void __launch_bounds__(128) selscan_bwd_fast_kernel(ScanParams p) {
     {
         float *dst = p.part_par + ((size_t)(b * p.nseg + seg) * 18) * p.ED + c;
 #pragma unroll
-        for (int q = 0; q < kPairs; ++q) {
+        for (int q = 0; q < NP; ++q) {
             const float2 dA = sdA[q * 32 + lane];
-            dst[(size_t)(2 * q) * p.ED] = dA.x;
-            dst[(size_t)(2 * q + 1) * p.ED] = dA.y;
+            dst[(size_t)(2 * (half * NP + q)) * p.ED] = dA.x;
+            dst[(size_t)(2 * (half * NP + q) + 1) * p.ED] = dA.y;
         }
-        dst[(size_t)16 * p.ED] = dD_acc;
-        dst[(size_t)17 * p.ED] = dbias_acc;
+        if (P == 2) {
+            dD_acc += __shfl_xor_sync(0xffffffffu, dD_acc, 1);
+            dbias_acc += __shfl_xor_sync(0xffffffffu, dbias_acc, 1);
+        }
+        if (half == 0) {
+            dst[(size_t)16 * p.ED] = dD_acc;
+            dst[(size_t)17 * p.ED] = dbias_acc;
+        }
     }
 }
 

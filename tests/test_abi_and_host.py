@@ -1,0 +1,161 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/gfe_mamba_b200.h declares (no compute
+without a GPU), size queries answer, the Python surface mirrors the reference (names, defaults, state-dict keys,
+seeded initialisation), and the product path refuses CPU tensors instead of falling back."""
+import ctypes
+import dataclasses
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "gfe_mamba_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"GFE_API\s+[\w\s\*]+?\b(gfe_\w+)\s*\(", src)))
+
+
+def test_header_declares_expected_entry_points():
+    syms = _declared_symbols()
+    for must in ("gfe_pscan_fwd", "gfe_pscan_bwd", "gfe_selscan_fwd", "gfe_selscan_bwd", "gfe_conv1d_silu_fwd",
+                 "gfe_conv1d_silu_bwd", "gfe_conv1d_step", "gfe_ssm_step", "gfe_version", "gfe_last_error_string"):
+        assert must in syms
+    assert len(syms) >= 19
+
+
+def test_library_exports_every_declared_symbol():
+    from gfe_mamba_b200 import _native
+    raw = ctypes.CDLL(_native.LIB_PATH)
+    for name in _declared_symbols():
+        assert hasattr(raw, name), f"{name} declared in the header but not exported"
+    lib = _native.lib()                      # also checks every signature in the ctypes table resolves
+    assert set(_native.SIGNATURES) == set(_declared_symbols())
+    assert lib.gfe_version() == 100
+    assert lib.gfe_timing_kernel_count() == 15 and lib.gfe_timing_kernel_name(3) == b"selscan_bwd"
+
+
+def test_size_queries_without_gpu():
+    from gfe_mamba_b200 import _native
+    lib = _native.lib()
+    B, L, ED, N = 16, 4096, 1536, 16
+    states = B * (L // 16) * ED * N * 4
+    assert lib.gfe_selscan_ckpt_bytes(B, L, ED, N) == states + B * L * ED * 4
+    assert lib.gfe_selscan_ckpt_bytes(B, L, ED, 8) == 0            # unsupported d_state -> 0
+    assert lib.gfe_selscan_bwd_workspace_bytes(B, L, ED, N) >= (ED // 32) * B * L * 32 * 4
+    assert lib.gfe_selscan_fwd_workspace_bytes(B, L, ED, N) == 0    # enough warps: no L split
+    assert lib.gfe_selscan_fwd_workspace_bytes(1, 65536, 1024, N) > 0   # cfg4 splits L
+    assert lib.gfe_pscan_workspace_bytes(32, 256, 512, 16) == 0
+    assert lib.gfe_pscan_workspace_bytes(1, 65536, 4, 16) > 0
+    assert lib.gfe_conv1d_bwd_workspace_bytes(2, 130, 64, 4) == 2 * 3 * 5 * 64 * 4
+
+
+def test_argument_validation_without_gpu():
+    """Bad arguments are rejected before any launch, with a message."""
+    from gfe_mamba_b200 import _native
+    lib = _native.lib()
+    a = _native.SelscanArgs()
+    assert lib.gfe_selscan_fwd(ctypes.byref(a), None) == -1
+    assert b"shape" in lib.gfe_last_error_string()
+    a.batch, a.seqlen, a.d_inner, a.d_state = 1, 8, 32, 8
+    assert lib.gfe_selscan_fwd(ctypes.byref(a), None) == -3
+    assert b"d_state" in lib.gfe_last_error_string()
+    assert lib.gfe_pscan_fwd(None, None, None, 1, 1, 1, 1, None, 0, None) == -1
+    assert lib.gfe_conv1d_silu_fwd(None, 0, 0, None, None, None, 0, 0, 1, 1, 1, 4, 0, None) == -1
+
+
+def test_selscan_args_struct_matches_header_field_order():
+    from gfe_mamba_b200 import _native
+    src = open(os.path.join(ROOT, "include", "gfe_mamba_b200.h")).read()
+    start = src.index("typedef struct gfe_selscan_args {") + len("typedef struct gfe_selscan_args {")
+    body = src[start:src.index("} gfe_selscan_args;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl or decl.startswith("typedef"):
+            continue
+        decl = re.sub(r"^(const\s+)?(void|float|int32_t|uint32_t|int64_t|size_t)\s*", "", decl)
+        names += [n.strip().lstrip("*") for n in decl.split(",")]
+    assert names == [f[0] for f in _native.SelscanArgs._fields_]
+
+
+def test_config_mirrors_reference():
+    from cross_atten.mamba import MambaConfig
+    cfg = MambaConfig(d_model=768, n_layers=2)
+    assert (cfg.d_inner, cfg.dt_rank, cfg.d_state, cfg.d_conv, cfg.expand_factor) == (1536, 48, 16, 4, 2)
+    assert cfg.pscan is True and cfg.use_cuda is False and cfg.bias is False and cfg.conv_bias is True
+    fields = [f.name for f in dataclasses.fields(cfg)]
+    assert fields == ["d_model", "n_layers", "dt_rank", "d_state", "expand_factor", "d_conv", "dt_min", "dt_max", "dt_init",
+                      "dt_scale", "rms_norm_eps", "bias", "conv_bias", "inner_layernorms", "pscan", "use_cuda"]
+    assert MambaConfig.dt_init_floor == 1e-4 and "dt_init_floor" not in fields     # class attribute, as in the reference
+    assert MambaConfig(d_model=512, n_layers=6, use_cuda=True).use_cuda is True    # mamba_transformer.py:65
+
+
+def test_state_dict_keys_and_seeded_init_match_reference(golden_dir):
+    """Same parameter names/shapes AND the same values under the same seed as the reference (mamba.py:126-168)."""
+    from cross_atten.mamba import MambaBlock, MambaConfig
+    g = dict(np.load(os.path.join(golden_dir, "block_small.npz")))
+    torch.manual_seed(303)                                   # tests/golden/make_golden.py: gen_block
+    blk = MambaBlock(MambaConfig(d_model=16, n_layers=1))
+    with torch.no_grad():
+        blk.A_log.add_(0.1 * torch.randn_like(blk.A_log))
+        blk.D.add_(0.1 * torch.randn_like(blk.D))
+    sd = blk.state_dict()
+    assert sorted(sd) == sorted(k[3:] for k in g if k.startswith("sd."))
+    for k, v in sd.items():
+        assert np.array_equal(v.numpy(), g["sd." + k]), k
+    assert blk.A_log._no_weight_decay and blk.D._no_weight_decay
+
+
+def test_mamba_state_dict_layout(golden_dir):
+    from cross_atten.mamba import Mamba, MambaConfig
+    g = dict(np.load(os.path.join(golden_dir, "mamba_cfg1.npz")))
+    m = Mamba(MambaConfig(d_model=128, n_layers=2, inner_layernorms=False))
+    want = {k[3:]: v.shape for k, v in g.items() if k.startswith("sd.")}
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == want
+    m.load_state_dict({k: torch.from_numpy(g["sd." + k]) for k in want}, strict=True)
+    j = Mamba(MambaConfig(d_model=32, n_layers=1, inner_layernorms=True))
+    assert {"layers.0.mixer.dt_layernorm.weight", "layers.0.mixer.B_layernorm.weight",
+            "layers.0.mixer.C_layernorm.weight"} <= set(j.state_dict())
+
+
+def test_drop_in_module_names():
+    import cross_atten.mamba as m
+    import cross_atten.pscan as ps
+    for name in ("MambaConfig", "Mamba", "ResidualBlock", "MambaBlock", "RMSNorm", "pscan"):
+        assert hasattr(m, name)
+    for name in ("pscan", "PScan", "npo2", "pad_npo2"):
+        assert hasattr(ps, name)
+    assert ps.npo2(1858) == 2048 and ps.npo2(4096) == 4096 and ps.npo2(1) == 1
+    assert tuple(ps.pad_npo2(torch.zeros(2, 5, 3, 4)).shape) == (2, 8, 3, 4)
+    assert os.path.abspath(m.__file__).startswith(ROOT)
+
+
+def test_no_cpu_fallback():
+    from cross_atten.mamba import Mamba, MambaConfig
+    from cross_atten.pscan import pscan
+    from gfe_mamba_b200 import causal_conv1d_silu, selective_scan_fn
+    m = Mamba(MambaConfig(d_model=16, n_layers=1))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.randn(1, 4, 16))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pscan(torch.rand(1, 4, 2, 2), torch.rand(1, 4, 2, 2))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        causal_conv1d_silu(torch.randn(1, 4, 8), torch.randn(8, 1, 4), None)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        selective_scan_fn(torch.randn(1, 4, 32), torch.randn(1, 4, 32), torch.zeros(32, 16), torch.randn(1, 4, 16),
+                          torch.randn(1, 4, 16), torch.ones(32))
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under gfe_mamba_b200/ or cross_atten/ may reference it."""
+    for pkg in ("gfe_mamba_b200", "cross_atten"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, pkg)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h")):
+                    txt = open(os.path.join(dirpath, f)).read()
+                    assert "oracle" not in txt.lower(), os.path.join(dirpath, f)
