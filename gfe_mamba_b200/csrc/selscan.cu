@@ -25,36 +25,10 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "selscan_shared.cuh"
 
 namespace gfe {
 
-struct ScanParams {
-    int B, L, ED;
-    int nseg, seg_len, nchunks;
-    uint32_t flags;
-    const void *u, *delta, *z, *Bm, *Cm;
-    int64_t u_bs, u_rs, d_bs, d_rs, z_bs, z_rs, B_bs, B_rs, C_bs, C_rs;
-    const float *A_log, *D, *dt_bias;
-    void *out;
-    int64_t o_bs, o_rs;
-    float *last_state;
-    float2 *ckpt;   // [B][nchunks][8][ED]
-    void *ysave;    // [B][L][ED] activation dtype: y before the gate (fast kernels), lives behind ckpt
-    float2 *seg_h;  // [B][nseg][8][ED]  segment-local end state (fwd) / start carry (bwd)
-    float *seg_sd;  // [B][nseg][ED]     sum of delta over the segment
-    // backward
-    const void *dout;
-    int64_t do_bs, do_rs;
-    void *du, *ddelta, *dz, *dBm, *dCm;
-    int64_t du_bs, du_rs, dd_bs, dd_rs, dz_bs, dz_rs, dB_bs, dB_rs, dC_bs, dC_rs;
-    float *dA_log, *dD, *ddt_bias;
-    float *part_bc;   // [G][B][L][32]   per-warp dB|dC rows
-    float *part_par;  // [B][nseg][18][ED]
-    int G;            // ceil(ED / 32)
-};
-
-constexpr int kPairs = kNState / 2;
-constexpr int kRedStride = 34;  // padded row of the reduced dB|dC tile (bank-conflict free float2 writes)
 
 // lane < 16 stages B[t][lane], lane >= 16 stages C[t][lane-16] for the kChunk steps starting at tb
 template <typename T>
@@ -605,7 +579,7 @@ __global__ void __launch_bounds__(256) selscan_bwd_finalize_bc_kernel(ScanParams
     const int64_t row = idx >> 5;
     const int n = (int)(idx & 31);
     float acc = 0.f;
-    const float *src = p.part_bc + idx;
+    const float *src = p.part_bc + (p.bc_interleaved ? (idx & ~(int64_t)31) + 2 * (n & 15) + (n >> 4) : idx);
     for (int g = 0; g < p.G; ++g) acc += __ldcs(src + (size_t)g * rows * 32);
     const int64_t b = row / p.L, t = row % p.L;
     if (n < 16)
@@ -798,6 +772,9 @@ static int launch_fwd(const gfe_selscan_args *a, cudaStream_t st) {
     return check_launch("selscan_fwd");
 }
 
+template <typename T>
+static int launch_finalize_t(const gfe_selscan_args *a, ScanParams &p, cudaStream_t st);
+
 template <typename T, bool HAS_Z>
 static int launch_bwd_z(const gfe_selscan_args *a, ScanParams &p, const SegPlan &sp, cudaStream_t st) {
     const int W = warps_per_cta();
@@ -832,15 +809,28 @@ static int launch_bwd_z(const gfe_selscan_args *a, ScanParams &p, const SegPlan 
     }
     int rc = check_launch("selscan_bwd");
     if (rc != GFE_OK) return rc;
+    return launch_finalize_t<T>(a, p, st);
+}
 
+// dB|dC and parameter-gradient finalize kernels, shared with the v2 backward (selscan_v2_bwd.cu)
+template <typename T>
+static int launch_finalize_t(const gfe_selscan_args *a, ScanParams &p, cudaStream_t st) {
     const int64_t nbc = (int64_t)a->batch * a->seqlen * 32;
     { ScopedKernelTimer tm(K_SELSCAN_BWD_FIN_BC, st);
       selscan_bwd_finalize_bc_kernel<T><<<(unsigned)ceil_div64(nbc, 256), 256, 0, st>>>(p); }
-    rc = check_launch("selscan_bwd_finalize_bc");
+    int rc = check_launch("selscan_bwd_finalize_bc");
     if (rc != GFE_OK) return rc;
     { ScopedKernelTimer tm(K_SELSCAN_BWD_FIN_PAR, st);
       selscan_bwd_finalize_par_kernel<<<dim3((a->d_inner + 127) / 128, 18), 128, 0, st>>>(p); }
     return check_launch("selscan_bwd_finalize_par");
+}
+
+void launch_bwd_finalize(const gfe_selscan_args *a, ScanParams &p, cudaStream_t st, int &rc) {
+    switch (a->dtype) {
+        case GFE_F32: rc = launch_finalize_t<float>(a, p, st); break;
+        case GFE_BF16: rc = launch_finalize_t<__nv_bfloat16>(a, p, st); break;
+        default: rc = launch_finalize_t<__half>(a, p, st); break;
+    }
 }
 
 template <typename T>
@@ -876,16 +866,20 @@ extern "C" {
 GFE_API size_t gfe_selscan_ckpt_bytes(int B, int L, int ED, int N) {
     if (B <= 0 || L <= 0 || ED <= 0 || N != gfe::kNState) return 0;
     // chunk-start states (fp32) + y before the gate (up to 4 bytes per element)
+    if (gfe::v2_applicable(B, L, ED))
+        return (size_t)B * ((L + gfe::kCkptV2 - 1) / gfe::kCkptV2) * ED * gfe::kNState * sizeof(float) + (size_t)B * L * ED * sizeof(float);
     return gfe::ckpt_state_bytes(B, L, ED) + (size_t)B * L * ED * sizeof(float);
 }
 
 GFE_API size_t gfe_selscan_fwd_workspace_bytes(int B, int L, int ED, int N) {
     if (B <= 0 || L <= 0 || ED <= 0 || N != gfe::kNState) return 0;
+    if (gfe::v2_applicable(B, L, ED)) return gfe::v2_fwd_workspace_bytes(B, L, ED);
     return gfe::fwd_ws_layout(B, L, ED, gfe::plan_segments(B, L, ED)).total;
 }
 
 GFE_API size_t gfe_selscan_bwd_workspace_bytes(int B, int L, int ED, int N) {
     if (B <= 0 || L <= 0 || ED <= 0 || N != gfe::kNState) return 0;
+    if (gfe::v2_applicable(B, L, ED)) return gfe::v2_bwd_workspace_bytes(B, L, ED);
     return gfe::bwd_ws_layout(B, L, ED, gfe::plan_segments(B, L, ED)).total;
 }
 
@@ -893,6 +887,7 @@ GFE_API int gfe_selscan_fwd(const gfe_selscan_args *a, void *stream) {
     int rc = gfe::validate_common(a, false);
     if (rc != GFE_OK) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (gfe::v2_applicable(a->batch, a->seqlen, a->d_inner)) return gfe::v2_launch_fwd(a, st);
     switch (a->dtype) {
         case GFE_F32: return gfe::launch_fwd<float>(a, st);
         case GFE_BF16: return gfe::launch_fwd<__nv_bfloat16>(a, st);
@@ -904,6 +899,7 @@ GFE_API int gfe_selscan_bwd(const gfe_selscan_args *a, void *stream) {
     int rc = gfe::validate_common(a, true);
     if (rc != GFE_OK) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (gfe::v2_applicable(a->batch, a->seqlen, a->d_inner)) return gfe::v2_launch_bwd(a, st);
     switch (a->dtype) {
         case GFE_F32: return gfe::launch_bwd<float>(a, st);
         case GFE_BF16: return gfe::launch_bwd<__nv_bfloat16>(a, st);

@@ -27,95 +27,9 @@
 #pragma once
 
 #include "common.cuh"
+#include "selscan_shared.cuh"
 
 namespace gfe {
-
-// ---- cp.async helpers -------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-template <int BYTES>
-__device__ __forceinline__ void cp_async(uint32_t dst, const void *src) {
-    if constexpr (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-    else if constexpr (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
-    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// Copy up to kChunk rows of ROW_ELEMS contiguous elements (row stride rs elements) into a dense shared tile.
-template <typename T, int CPB, int ROW_ELEMS>
-__device__ __forceinline__ void tile_issue(uint32_t dst, const T *src, int64_t rs, int nrows, int lane, int dst_row_bytes,
-                                           int dst_col_byte_off) {
-    constexpr int RB = ROW_ELEMS * (int)sizeof(T);   // bytes per source row
-    constexpr int PPR = RB / CPB;                     // pieces per row
-    constexpr int TOTAL = kChunk * PPR;
-    const char *s = reinterpret_cast<const char *>(src);
-#pragma unroll
-    for (int i0 = 0; i0 < TOTAL; i0 += 32) {
-        const int i = i0 + lane;
-        const int row = i / PPR, piece = i % PPR;
-        if ((TOTAL % 32 == 0 || i < TOTAL) && row < nrows)
-            cp_async<CPB>(dst + row * dst_row_bytes + dst_col_byte_off + piece * CPB, s + (int64_t)row * rs * (int64_t)sizeof(T) + piece * CPB);
-    }
-}
-
-// exp2 of two non-positive arguments on the FMA pipe: Cody-Waite split + degree-5 minimax (max rel err 2.3e-7
-// in fp32, same class as ex2.approx), exponent inserted with integer adds.
-__device__ __forceinline__ float2 ex2_poly2(float2 x) {
-    x.x = fmaxf(x.x, -125.0f);
-    x.y = fmaxf(x.y, -125.0f);
-    const float2 magic = make_float2(12582912.0f, 12582912.0f);
-    const float2 t = fadd2(x, magic);
-    const float2 n = fadd2(t, make_float2(-12582912.0f, -12582912.0f));
-    const float2 f = fadd2(x, make_float2(-n.x, -n.y));
-    float2 p = make_float2(0.001327647129073739f, 0.001327647129073739f);
-    p = ffma2(p, f, make_float2(0.009675540961325169f, 0.009675540961325169f));
-    p = ffma2(p, f, make_float2(0.05550713092088699f, 0.05550713092088699f));
-    p = ffma2(p, f, make_float2(0.24022120237350464f, 0.24022120237350464f));
-    p = ffma2(p, f, make_float2(0.6931469440460205f, 0.6931469440460205f));
-    p = ffma2(p, f, make_float2(1.0000001192092896f, 1.0000001192092896f));
-    return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23)),
-                       __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23)));
-}
-
-// log1p(e) for 0 <= e < 0.5 via 2 atanh(e / (2 + e))
-__device__ __forceinline__ float log1p_small(float e) {
-    const float s = e * rcp_approx(2.0f + e);
-    const float s2 = s * s;
-    float p = fmaf(s2, 1.0f / 9.0f, 1.0f / 7.0f);
-    p = fmaf(s2, p, 1.0f / 5.0f);
-    p = fmaf(s2, p, 1.0f / 3.0f);
-    p = fmaf(s2, p, 1.0f);
-    return 2.0f * s * p;
-}
-
-// softplus for a group of G steps, branch-free per lane; the log1p formulation is chosen by a warp-uniform vote.
-// x[i] -> dl[i]; optionally sig[i] = sigmoid(x[i]).
-template <int G, bool WANT_SIG>
-__device__ __forceinline__ void softplus_group(const float (&x)[G], float (&dl)[G], float (&sig)[G]) {
-    float e[G];
-    bool any_big = false;
-#pragma unroll
-    for (int i = 0; i < G; ++i) {
-        e[i] = ex2_approx(fminf(x[i], 30.0f) * kLog2e);
-        any_big |= e[i] >= 0.5f;
-    }
-#pragma unroll
-    for (int i = 0; i < G; ++i) dl[i] = log1p_small(fminf(e[i], 0.5f));
-    if (__any_sync(0xffffffffu, any_big)) {
-#pragma unroll
-        for (int i = 0; i < G; ++i) {
-            const float big = kLn2 * lg2_approx(1.0f + e[i]);
-            dl[i] = e[i] >= 0.5f ? big : dl[i];
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < G; ++i) {
-        if (WANT_SIG) sig[i] = x[i] > 20.0f ? 1.0f : e[i] * rcp_approx(1.0f + e[i]);
-        dl[i] = x[i] > 20.0f ? x[i] : dl[i];
-    }
-}
 
 constexpr int kGroup = 4;          // steps per rolled-loop iteration
 

@@ -42,11 +42,13 @@ def test_size_queries_without_gpu():
     from gfe_mamba_b200 import _native
     lib = _native.lib()
     B, L, ED, N = 16, 4096, 1536, 16
-    states = B * (L // 16) * ED * N * 4
+    states = B * (L // 8) * ED * N * 4                              # chained kernels checkpoint every 8 steps
     assert lib.gfe_selscan_ckpt_bytes(B, L, ED, N) == states + B * L * ED * 4
+    assert lib.gfe_selscan_ckpt_bytes(1, 65536, 1024, N) == (65536 // 16) * 1024 * N * 4 + 65536 * 1024 * 4   # L-split path: 16
     assert lib.gfe_selscan_ckpt_bytes(B, L, ED, 8) == 0            # unsupported d_state -> 0
     assert lib.gfe_selscan_bwd_workspace_bytes(B, L, ED, N) >= (ED // 32) * B * L * 32 * 4
-    assert lib.gfe_selscan_fwd_workspace_bytes(B, L, ED, N) == 0    # enough warps: no L split
+    # chained segments: counter + flags + one (B, ED, N) fp32 carry; far below one activation tensor
+    assert B * ED * N * 4 < lib.gfe_selscan_fwd_workspace_bytes(B, L, ED, N) < B * L * ED
     assert lib.gfe_selscan_fwd_workspace_bytes(1, 65536, 1024, N) > 0   # cfg4 splits L
     assert lib.gfe_pscan_workspace_bytes(32, 256, 512, 16) == 0
     assert lib.gfe_pscan_workspace_bytes(1, 65536, 4, 16) > 0
