@@ -9,7 +9,10 @@ import os
 import threading
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libgfe_mamba_b200.so")
+# GFE_LIB_VARIANT=<tag> loads lib/libgfe_mamba_b200.<tag>.so (A/B builds of the same sources, `build.py --tag=`); it
+# must exist -- there is no fallback either way.
+_VARIANT = os.environ.get("GFE_LIB_VARIANT", "")
+LIB_PATH = os.path.join(_PKG, "lib", f"libgfe_mamba_b200.{_VARIANT}.so" if _VARIANT else "libgfe_mamba_b200.so")
 
 GFE_F32, GFE_BF16, GFE_F16 = 0, 1, 2
 GFE_FLAG_DELTA_SOFTPLUS = 1

@@ -20,7 +20,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 OBJDIR = os.path.join(PKG, "build")
 LIB = os.path.join(LIBDIR, "libgfe_mamba_b200.so")
-SOURCES = ["api.cu", "selscan.cu", "selscan_v2_fwd.cu", "selscan_v2_bwd.cu", "pscan.cu", "conv1d.cu", "step.cu"]
+SOURCES = ["api.cu", "selscan.cu", "selscan_v2_fwd.cu", "selscan_v2_bwd.cu", "selscan_v3_fwd.cu", "selscan_v3_bwd.cu", "pscan.cu", "conv1d.cu", "step.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -54,7 +54,12 @@ def _stale(target: str, deps: list) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, defs: tuple = (), tag: str = "") -> str:
+    """`defs`/`tag` build an A/B variant (extra -D flags) into lib/libgfe_mamba_b200.<tag>.so; development only."""
+    global OBJDIR, LIB
+    if tag:
+        OBJDIR = os.path.join(PKG, "build", tag)
+        LIB = os.path.join(LIBDIR, f"libgfe_mamba_b200.{tag}.so")
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
@@ -66,7 +71,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         s = os.path.join(CSRC, src)
         o = os.path.join(OBJDIR, src.replace(".cu", ".o"))
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc] + ccbin + NVCC_FLAGS + ["-c", s, "-o", o]
+            cmd = [nvcc] + ccbin + NVCC_FLAGS + [f"-D{d}" for d in defs] + ["-c", s, "-o", o]
             r = subprocess.run(cmd, capture_output=True, text=True)
             with open(o + ".log", "w") as f:
                 f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
@@ -87,5 +92,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    _defs = tuple(a[2:] for a in sys.argv if a.startswith("-D"))
+    _tag = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--tag=")), "")
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defs=_defs, tag=_tag)
     print(path)

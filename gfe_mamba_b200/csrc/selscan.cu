@@ -26,6 +26,7 @@
 
 #include "common.cuh"
 #include "selscan_shared.cuh"
+#include "selscan_v3.cuh"
 
 namespace gfe {
 
@@ -579,7 +580,9 @@ __global__ void __launch_bounds__(256) selscan_bwd_finalize_bc_kernel(ScanParams
     const int64_t row = idx >> 5;
     const int n = (int)(idx & 31);
     float acc = 0.f;
-    const float *src = p.part_bc + (p.bc_interleaved ? (idx & ~(int64_t)31) + 2 * (n & 15) + (n >> 4) : idx);
+    const int64_t rbase = idx & ~(int64_t)31;
+    const float *src = p.part_bc + (p.bc_interleaved == 2 ? rbase + ((n >> 4) * 2 + (n & 1)) * 8 + ((n & 15) >> 1)   // v3: [dB even | dB odd | dC even | dC odd]
+                                    : p.bc_interleaved ? rbase + 2 * (n & 15) + (n >> 4) : idx);
     for (int g = 0; g < p.G; ++g) acc += __ldcs(src + (size_t)g * rows * 32);
     const int64_t b = row / p.L, t = row % p.L;
     if (n < 16)
@@ -866,19 +869,21 @@ extern "C" {
 GFE_API size_t gfe_selscan_ckpt_bytes(int B, int L, int ED, int N) {
     if (B <= 0 || L <= 0 || ED <= 0 || N != gfe::kNState) return 0;
     // chunk-start states (fp32) + y before the gate (up to 4 bytes per element)
-    if (gfe::v2_applicable(B, L, ED))
+    if (gfe::v3_shape_ok(B, L, ED) || gfe::v2_applicable(B, L, ED))
         return (size_t)B * ((L + gfe::kCkptV2 - 1) / gfe::kCkptV2) * ED * gfe::kNState * sizeof(float) + (size_t)B * L * ED * sizeof(float);
     return gfe::ckpt_state_bytes(B, L, ED) + (size_t)B * L * ED * sizeof(float);
 }
 
 GFE_API size_t gfe_selscan_fwd_workspace_bytes(int B, int L, int ED, int N) {
     if (B <= 0 || L <= 0 || ED <= 0 || N != gfe::kNState) return 0;
+    if (gfe::v3_shape_ok(B, L, ED)) return gfe::v3_fwd_workspace_bytes(B, L, ED);
     if (gfe::v2_applicable(B, L, ED)) return gfe::v2_fwd_workspace_bytes(B, L, ED);
     return gfe::fwd_ws_layout(B, L, ED, gfe::plan_segments(B, L, ED)).total;
 }
 
 GFE_API size_t gfe_selscan_bwd_workspace_bytes(int B, int L, int ED, int N) {
     if (B <= 0 || L <= 0 || ED <= 0 || N != gfe::kNState) return 0;
+    if (gfe::v3_shape_ok(B, L, ED)) return gfe::v3_bwd_workspace_bytes(B, L, ED);
     if (gfe::v2_applicable(B, L, ED)) return gfe::v2_bwd_workspace_bytes(B, L, ED);
     return gfe::bwd_ws_layout(B, L, ED, gfe::plan_segments(B, L, ED)).total;
 }
@@ -887,6 +892,7 @@ GFE_API int gfe_selscan_fwd(const gfe_selscan_args *a, void *stream) {
     int rc = gfe::validate_common(a, false);
     if (rc != GFE_OK) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (gfe::v3_shape_ok(a->batch, a->seqlen, a->d_inner)) return gfe::v3_launch_fwd(a, st);
     if (gfe::v2_applicable(a->batch, a->seqlen, a->d_inner)) return gfe::v2_launch_fwd(a, st);
     switch (a->dtype) {
         case GFE_F32: return gfe::launch_fwd<float>(a, st);
@@ -899,6 +905,7 @@ GFE_API int gfe_selscan_bwd(const gfe_selscan_args *a, void *stream) {
     int rc = gfe::validate_common(a, true);
     if (rc != GFE_OK) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (gfe::v3_shape_ok(a->batch, a->seqlen, a->d_inner)) return gfe::v3_launch_bwd(a, st);
     if (gfe::v2_applicable(a->batch, a->seqlen, a->d_inner)) return gfe::v2_launch_bwd(a, st);
     switch (a->dtype) {
         case GFE_F32: return gfe::launch_bwd<float>(a, st);
