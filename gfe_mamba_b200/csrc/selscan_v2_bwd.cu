@@ -41,7 +41,9 @@ constexpr int kBwdNT = 128;    // 4 lanes per channel: lane (c, q) owns states 4
 constexpr int kBwdWarps = kBwdNT / 32;
 constexpr int kRedRow = 36;    // padded row (floats) of the per-warp dB|dC tile: [t][n]{dB, dC}
 constexpr int kSPlane = 36;    // padded plane (float2) of the {S1, S2} partials: [t][q][c]
-constexpr int kDDPlane = kChunk * 16 + 4;   // float4 per parity plane of the {dl, dl, dl*u, dl*u} slots (+64 B skew)
+constexpr int kDDPlane = kChunk * 16 + 4;   // float4 per parity plane of the {dl, dl*u, dy, 0} slots (+64 B skew)
+constexpr int kBCPlane = kChunk * 8 + 4;    // float4 per B|C plane; the 64 B skew keeps the natural and the pair-swapped plane (read by
+                                            // the even / odd channels of one quarter-warp) on disjoint banks
 
 template <typename T, bool HAS_Z>
 struct BwdV2Smem {
@@ -50,11 +52,10 @@ struct BwdV2Smem {
     static constexpr int kNTile = HAS_Z ? 5 : 3;
     static constexpr int kBCRaw = kChunk * kNState * (int)sizeof(T);    // one of B, C
     static constexpr int kStage = kNTile * kTile + 2 * kBCRaw;
-    static constexpr int kOffDD = kStages * kStage;                     // float4 [2 parity][16][16] {dl, dl, dl*u, dl*u}
-    static constexpr int kOffDy = kOffDD + 2 * kDDPlane * 16;           // float2 [16][32] {dy, dy}
-    static constexpr int kOffEpi = kOffDy + kChunk * 32 * 8;            // float2 [16][32] {u, softplus'}
-    static constexpr int kOffBC = kOffEpi + kChunk * 32 * 8;            // float4 [2][16][8] B quads | C quads, natural / pair-swapped
-    static constexpr int kOffS = kOffBC + 2 * kChunk * 8 * 16;          // float2 [16][4][36] {S1, S2} partial per lane
+    static constexpr int kOffDD = kStages * kStage;                     // float4 [2 parity][16][16] {dl, dl*u, dy, 0}
+    static constexpr int kOffEpi = kOffDD + 2 * kDDPlane * 16;          // float2 [16][32] {u, softplus'}
+    static constexpr int kOffBC = kOffEpi + kChunk * 32 * 8;            // float4 [2][16][8] (+64 B skew) B quads | C quads, natural / pair-swapped
+    static constexpr int kOffS = kOffBC + 2 * kBCPlane * 16;            // float2 [16][4][36] {S1, S2} partial per lane
     static constexpr int kOffRed = kOffS + kChunk * 4 * kSPlane * 8;    // float  [4 warps][16][36] per-warp dB|dC rows
     static constexpr int kTotal = kOffRed + kBwdWarps * kChunk * kRedRow * 4;
 };
@@ -71,7 +72,6 @@ __global__ void __launch_bounds__(kBwdNT, 3) selscan_bwd_v2_kernel(ScanParams p,
     const int ip = tid & 15, ir = tid >> 4;  // item mapping: channels 2 ip, 2 ip + 1; rows ir and ir + 8
 
     float4 *sDD = reinterpret_cast<float4 *>(smem + SM::kOffDD);
-    float4 *sDy4 = reinterpret_cast<float4 *>(smem + SM::kOffDy);     // {dy0, dy0, dy1, dy1} per channel pair
     float4 *sEpi4 = reinterpret_cast<float4 *>(smem + SM::kOffEpi);   // {u0, sg0, u1, sg1}
     float4 *sBC = reinterpret_cast<float4 *>(smem + SM::kOffBC);
     float2 *sS = reinterpret_cast<float2 *>(smem + SM::kOffS);
@@ -82,8 +82,7 @@ __global__ void __launch_bounds__(kBwdNT, 3) selscan_bwd_v2_kernel(ScanParams p,
 
     // recurrence-side shared pointers (fixed for the whole kernel)
     const float4 *dd_r = sDD + (rc & 1) * kDDPlane + (rc >> 1);
-    const float2 *dy_r = reinterpret_cast<const float2 *>(sDy4) + rc;
-    const float4 *bc_r = sBC + sw * (kChunk * 8) + rq;
+    const float4 *bc_r = sBC + sw * kBCPlane + rq;
     float2 *s_w = sS + rq * kSPlane + rc;
     const bool up8 = (lane & 8) != 0, up16 = (lane & 16) != 0;
     float *red_w = sRed + warp * (kChunk * kRedRow) + (up16 ? kRedRow : 0) + 2 * (4 * rq + (up8 ? 2 : 0) + sw);
@@ -212,9 +211,8 @@ __global__ void __launch_bounds__(kBwdNT, 3) selscan_bwd_v2_kernel(ScanParams p,
                     }
                 }
                 const float dlu0 = dl0 * u0, dlu1 = dl1 * u1;
-                sDD[t * 16 + ip] = make_float4(dl0, dl0, dlu0, dlu0);               // even channel
-                sDD[kDDPlane + t * 16 + ip] = make_float4(dl1, dl1, dlu1, dlu1);    // odd channel
-                sDy4[t * 16 + ip] = make_float4(dy0, dy0, dy1, dy1);
+                sDD[t * 16 + ip] = make_float4(dl0, dlu0, dy0, 0.f);               // even channel
+                sDD[kDDPlane + t * 16 + ip] = make_float4(dl1, dlu1, dy1, 0.f);    // odd channel
                 sEpi4[t * 16 + ip] = make_float4(u0, sg[2 * ps], u1, sg[2 * ps + 1]);
             }
             {   // B|C rows -> fp32 quads, natural and pair-swapped order: [sw][t][B quads 0..3 | C quads 0..3]
@@ -226,7 +224,7 @@ __global__ void __launch_bounds__(kBwdNT, 3) selscan_bwd_v2_kernel(ScanParams p,
                     v = make_float4(lo.x, lo.y, hi.x, hi.y);
                 }
                 sBC[tid] = v;
-                sBC[kChunk * 8 + tid] = make_float4(v.y, v.x, v.w, v.z);
+                sBC[kBCPlane + tid] = make_float4(v.y, v.x, v.w, v.z);
             }
         };
 
@@ -248,7 +246,6 @@ __global__ void __launch_bounds__(kBwdNT, 3) selscan_bwd_v2_kernel(ScanParams p,
                 const int jo = half * kCkptV2;
                 if (tb + jo >= t1) continue;          // block-uniform: the half lies beyond the sequence
                 const float4 *dd_p = dd_r + jo * 16;
-                const float2 *dy_p = dy_r + jo * CPC;
                 const float4 *bc_p = bc_r + jo * 8;
                 float2 *s_p = s_w + jo * (4 * kSPlane);
                 float *red_p = red_w + jo * kRedRow;
@@ -260,9 +257,9 @@ __global__ void __launch_bounds__(kBwdNT, 3) selscan_bwd_v2_kernel(ScanParams p,
                 }
 #pragma unroll
                 for (int j = 0; j < kCkptV2; ++j) {   // forward sweep: re-derive the states of this half chunk
-                    const float4 dd = dd_p[j * 16];
+                    const float2 dd = *reinterpret_cast<const float2 *>(dd_p + j * 16);   // {dl, dl*u}
                     const float4 B4 = bc_p[j * 8];
-                    const float2 dl2 = make_float2(dd.x, dd.y), du2 = make_float2(dd.z, dd.w);
+                    const float2 dl2 = splat2(dd.x), du2 = splat2(dd.y);   // scalar-broadcast operands (R.F32), no moves
                     a0[j] = ex2_2(fmul2(dl2, A2[0]));
                     a1[j] = ex2_2(fmul2(dl2, A2[1]));
                     h0[j + 1] = ffma2(a0[j], h0[j], fmul2(du2, make_float2(B4.x, B4.y)));
@@ -274,10 +271,9 @@ __global__ void __launch_bounds__(kBwdNT, 3) selscan_bwd_v2_kernel(ScanParams p,
 #pragma unroll
                     for (int jj = 1; jj >= 0; --jj) {
                         const int j = jb + jj;
-                        const float4 dd = dd_p[j * 16];
-                        const float2 dy2 = dy_p[j * CPC];
+                        const float4 dd = dd_p[j * 16];   // {dl, dl*u, dy, 0}
                         const float4 B4 = bc_p[j * 8], C4 = bc_p[j * 8 + 4];
-                        const float2 dl2 = make_float2(dd.x, dd.y), du2 = make_float2(dd.z, dd.w);
+                        const float2 dl2 = splat2(dd.x), du2 = splat2(dd.y), dy2 = splat2(dd.z);
                         const float2 gg0 = ffma2(make_float2(C4.x, C4.y), dy2, G[0]);   // g[t] = C dy + a[t+1] g[t+1]
                         const float2 gg1 = ffma2(make_float2(C4.z, C4.w), dy2, G[1]);
                         const float2 dc0 = fmul2(dy2, h0[j + 1]), dc1 = fmul2(dy2, h1[j + 1]);   // dC_t[n] += dy h[t]
@@ -332,8 +328,9 @@ __global__ void __launch_bounds__(kBwdNT, 3) selscan_bwd_v2_kernel(ScanParams p,
                     const float4 p0 = sp4[0], p1 = sp4[kSPlane / 2], p2 = sp4[kSPlane], p3 = sp4[3 * (kSPlane / 2)];
                     const float s1a = (p0.x + p1.x) + (p2.x + p3.x), s2a = ((p0.y + p1.y) + (p2.y + p3.y)) * kLn2;
                     const float s1b = (p0.z + p1.z) + (p2.z + p3.z), s2b = ((p0.w + p1.w) + (p2.w + p3.w)) * kLn2;
-                    const float dl0 = sDD[t * 16 + ip].x, dl1 = sDD[kDDPlane + t * 16 + ip].x;
-                    const float4 dy4 = sDy4[t * 16 + ip];
+                    const float4 dd0 = sDD[t * 16 + ip], dd1 = sDD[kDDPlane + t * 16 + ip];
+                    const float dl0 = dd0.x, dl1 = dd1.x;
+                    const float4 dy4 = make_float4(dd0.z, dd0.z, dd1.z, dd1.z);
                     const float4 e4 = sEpi4[t * 16 + ip];
                     const float draw0 = fmaf(s1a, e4.x, s2a) * e4.y, draw1 = fmaf(s1b, e4.z, s2b) * e4.w;   // d delta through softplus
                     stg_pair<T>(dub + (int64_t)(tb + t) * p.du_rs, fmaf(dl0, s1a, Dc.x * dy4.x), fmaf(dl1, s1b, Dc.y * dy4.z), vec);

@@ -270,9 +270,10 @@ __global__ void __launch_bounds__(32 * kV3MaxWarps, 1) selscan_fwd_v3_kernel(Sca
 // ---------------------------------------------------------------------------------------------------- host
 bool v3_shape_ok(int B, int L, int ED) {
     if (ED % 32 != 0) return false;
-    if (const char *e = getenv("GFE_SELSCAN_V3")) {   // A/B measurements only
-        if (e[0] == '0') return false;
-    }
+    // Opt-in only (GFE_SELSCAN_V3=1, A/B measurements): one warp per scheduler caps the FP32 pipe at half rate, the
+    // v3 pair measured 4.64 ms per cfg3 step against 3.46 ms for v2 (profiles/r01_ab_v2_v3.txt).
+    const char *e = getenv("GFE_SELSCAN_V3");
+    if (e == nullptr || e[0] != '1') return false;
     return plan_segments(B, L, ED).nseg == 1;   // enough (row, channel) chains; otherwise the L-split kernels
 }
 

@@ -1,0 +1,330 @@
+// selscan_v4_fwd.cu -- fused selective-scan forward, "v4": two channels x four states per lane.
+// Replaces mamba.py:255-256, 275-284, 220-222 of the reference (softplus -> discretise -> scan -> C.h -> D skip -> gate).
+//
+// What the v2 profile said (profiles/r01_ab_*): the forward was bound by the shared-memory data pipe and by issue slots,
+// not by HBM.  An LDS.128 costs ~2 pipe clocks whatever its address pattern (tools/microbench_lds.cu), so the number
+// of LDS per state-step is what matters, and half of v2's instructions were spent outside the recurrence.  Here
+//   * a lane owns the states 4q..4q+3 of TWO adjacent channels: the B and C quads it fetches feed eight state-steps
+//     instead of four, and {delta, delta*u} of both channels arrive in one LDS.128 (no splatted copies: ptxas folds a
+//     scalar operand of FFMA2/FMUL2 into the R.F32 broadcast form);
+//   * a CTA of 128 threads serves 64 channels; every thread stages exactly one 16-byte piece per tile with offsets
+//     computed once per unit, and the per-(t, channel pair) scalar work runs once per pair in the item mapping;
+//   * per lane and step: 3 LDS.128 + 16 packed FP32 ops + 8 exp2 (2 of them on the FMA pipe) + 1 STS.64 for 8
+//     state-steps (v2: 3 LDS.128 + 8 + 4 + 1 for 4).
+// Segment chaining (ChainSched), checkpoint layout ([b][t/8][c][16] fp32) and the saved y are exactly those of v2, so
+// the v2 backward kernel consumes what this kernel writes.
+#include "common.cuh"
+#include "selscan_shared.cuh"
+
+namespace gfe {
+
+constexpr int kV4CPC = 64;            // channels per CTA
+constexpr int kV4NT = 2 * kV4CPC;     // 128 threads: lane (pair, quad) owns 2 channels x 4 states
+constexpr int kV4YPlane = 36;         // float2 per (t, quad) plane of the partial C.h: 32 pairs + 32 B skew (conflict-free STS.64)
+
+template <typename T, bool HAS_Z>
+struct FwdV4Smem {
+    static constexpr int kStages = sizeof(T) == 4 ? 2 : 3;
+    static constexpr int kNTile = HAS_Z ? 3 : 2;
+    static constexpr int kTile = kChunk * kV4CPC * (int)sizeof(T);      // one of u, delta, z
+    static constexpr int kBCRaw = kChunk * kNState * (int)sizeof(T);     // one of B, C
+    static constexpr int kStage = kNTile * kTile + 2 * kBCRaw;
+    static constexpr int kOffDD = kStages * kStage;                      // float2 [16][64] {dl, dl*u}
+    static constexpr int kOffBC = kOffDD + kChunk * kV4CPC * 8;          // float4 [16][8]  B quads | C quads
+    static constexpr int kOffY = kOffBC + kChunk * 8 * 16;               // float2 [16][4][36] partial C.h of a channel pair
+    static constexpr int kTotal = kOffY + kChunk * 4 * kV4YPlane * 8;
+};
+
+template <typename T, bool HAS_Z, int CPB>
+__global__ void __launch_bounds__(kV4NT, 4) selscan_fwd_v4_kernel(ScanParams p, ChainSched cs) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int s_unit;
+    using SM = FwdV4Smem<T, HAS_Z>;
+    constexpr int NT = kV4NT, CPC = kV4CPC, NST = SM::kStages, NTILE = SM::kNTile;
+    constexpr int RB = CPC * (int)sizeof(T);          // bytes per tile row
+    constexpr int PPT = kChunk * RB / 16 / NT;        // 16-byte pieces per thread per activation tile (1 bf16, 2 fp32)
+    constexpr int BCP = kChunk * kNState * (int)sizeof(T) / 16;   // pieces per B (or C) tile: 32 bf16, 64 fp32
+    const int tid = threadIdx.x;
+    const int rp = tid >> 2, rq = tid & 3;     // recurrence mapping: channel pair in block (0..31), state quad
+    const int ip = tid & 31, ir = tid >> 5;    // item mapping: channel pair, rows ir + 4 i
+
+    float4 *sDD = reinterpret_cast<float4 *>(smem + SM::kOffDD);   // [t][pair] {dl0, dl0*u0, dl1, dl1*u1}
+    float4 *sBC = reinterpret_cast<float4 *>(smem + SM::kOffBC);
+    float2 *sY = reinterpret_cast<float2 *>(smem + SM::kOffY);
+    const bool sp = p.flags & GFE_FLAG_DELTA_SOFTPLUS;
+    const bool vec = p.flags & kFlagPairStores;
+    const int per_seg = p.B * cs.nblk;
+
+    const float4 *dd_r = sDD + rp;
+    const float4 *bc_r = sBC + rq;
+    float2 *y_w = sY + rq * kV4YPlane + rp;
+
+    // staging geometry of this thread (fixed): activation tiles and B|C tiles
+    const int srow = (tid * PPT) / (RB / 16), spiece = (tid * PPT) % (RB / 16);   // PPT consecutive pieces of one row
+    const bool bc_thread = tid < 2 * BCP;
+    const int bcsel = tid / BCP;                                      // 0: B, 1: C
+    const int bcrow = (tid % BCP) / (BCP / kChunk), bcpiece = (tid % BCP) % (BCP / kChunk);
+
+    for (;;) {
+        __syncthreads();   // every thread is done with the previous unit's shared memory
+        if (tid == 0) s_unit = atomicAdd(cs.counter, 1);
+        __syncthreads();
+        const int unit = s_unit;
+        if (unit >= cs.total) break;
+        const int seg = unit / per_seg;
+        const int rem = unit - seg * per_seg;
+        const int b = rem / cs.nblk;
+        const int c0 = (rem - b * cs.nblk) * CPC;
+        const int t0 = seg * cs.seg_len, t1 = min(p.L, t0 + cs.seg_len);
+        const int nch = (t1 - t0 + kChunk - 1) / kChunk;
+
+        const T *ub = reinterpret_cast<const T *>(p.u) + (int64_t)b * p.u_bs + c0;
+        const T *db = reinterpret_cast<const T *>(p.delta) + (int64_t)b * p.d_bs + c0;
+        const T *zb = HAS_Z ? reinterpret_cast<const T *>(p.z) + (int64_t)b * p.z_bs + c0 : nullptr;
+        const T *Bb = reinterpret_cast<const T *>(p.Bm) + (int64_t)b * p.B_bs;
+        const T *Cb = reinterpret_cast<const T *>(p.Cm) + (int64_t)b * p.C_bs;
+        T *ob = reinterpret_cast<T *>(p.out) + (int64_t)b * p.o_bs + c0 + 2 * ip;
+        T *yb = p.ysave ? reinterpret_cast<T *>(p.ysave) + (int64_t)b * p.L * p.ED + c0 + 2 * ip : nullptr;
+        // checkpoints [b][t / 8][c][16] fp32: this lane's quads of channels 2 rp and 2 rp + 1
+        float4 *ckq = p.ckpt ? reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.ckpt) +
+                                                          ((size_t)b * p.nchunks * p.ED + c0 + 2 * rp) * kNState) + rq : nullptr;
+        const size_t ck_step = (size_t)p.ED * (kNState / 4);
+
+        // per-thread source pointers of the staged pieces at row t0 (advanced by 16 rows per chunk)
+        const char *su, *sd, *sz = nullptr, *sbc = nullptr;
+        int64_t adv_u, adv_d, adv_z = 0, adv_bc = 0;
+        if constexpr (CPB == 16) {
+            su = reinterpret_cast<const char *>(ub + (int64_t)(t0 + srow) * p.u_rs) + spiece * 16;
+            sd = reinterpret_cast<const char *>(db + (int64_t)(t0 + srow) * p.d_rs) + spiece * 16;
+            adv_u = (int64_t)kChunk * p.u_rs * (int64_t)sizeof(T);
+            adv_d = (int64_t)kChunk * p.d_rs * (int64_t)sizeof(T);
+            if (HAS_Z) {
+                sz = reinterpret_cast<const char *>(zb + (int64_t)(t0 + srow) * p.z_rs) + spiece * 16;
+                adv_z = (int64_t)kChunk * p.z_rs * (int64_t)sizeof(T);
+            }
+            if (bc_thread) {
+                const int64_t rs = bcsel ? p.C_rs : p.B_rs;
+                sbc = reinterpret_cast<const char *>((bcsel ? Cb : Bb) + (int64_t)(t0 + bcrow) * rs) + bcpiece * 16;
+                adv_bc = (int64_t)kChunk * rs * (int64_t)sizeof(T);
+            }
+        }
+        const uint32_t dst_act = smem_u32(smem) + srow * RB + spiece * 16;
+        const uint32_t dst_bc = smem_u32(smem) + NTILE * SM::kTile + bcsel * SM::kBCRaw + (tid % BCP) * 16;
+
+        auto issue = [&](int k) {   // chunk k of this segment -> stage k % NST
+            if (k < nch) {
+                const int tb = t0 + k * kChunk;
+                const int nrows = min(kChunk, t1 - tb);
+                const uint32_t so = (k % NST) * SM::kStage;
+                if constexpr (CPB == 16) {
+                    if (srow < nrows) {
+#pragma unroll
+                        for (int i = 0; i < PPT; ++i) {
+                            cp_async<16>(dst_act + so + i * 16, su + (int64_t)k * adv_u + i * 16);
+                            cp_async<16>(dst_act + so + SM::kTile + i * 16, sd + (int64_t)k * adv_d + i * 16);
+                            if (HAS_Z) cp_async<16>(dst_act + so + 2 * SM::kTile + i * 16, sz + (int64_t)k * adv_z + i * 16);
+                        }
+                    }
+                    if (bc_thread && bcrow < nrows) cp_async<16>(dst_bc + so, sbc + (int64_t)k * adv_bc);
+                } else {
+                    unsigned char *s = smem + so;
+                    stage_tile<T, 0, CPC, NT>(s, ub + (int64_t)tb * p.u_rs, p.u_rs, nrows, tid);
+                    stage_tile<T, 0, CPC, NT>(s + SM::kTile, db + (int64_t)tb * p.d_rs, p.d_rs, nrows, tid);
+                    if (HAS_Z) stage_tile<T, 0, CPC, NT>(s + 2 * SM::kTile, zb + (int64_t)tb * p.z_rs, p.z_rs, nrows, tid);
+                    stage_tile<T, 0, kNState, NT>(s + NTILE * SM::kTile, Bb + (int64_t)tb * p.B_rs, p.B_rs, nrows, tid);
+                    stage_tile<T, 0, kNState, NT>(s + NTILE * SM::kTile + SM::kBCRaw, Cb + (int64_t)tb * p.C_rs, p.C_rs, nrows, tid);
+                }
+            }
+            cp_async_commit();
+        };
+#pragma unroll
+        for (int k = 0; k < NST; ++k) issue(k);
+
+        // per-thread constants: A of both channels (recurrence mapping), D and bias (item mapping)
+        float2 A2[2][2], h[2][2];
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(p.A_log + (size_t)(c0 + 2 * rp + ch) * kNState) + rq);
+            A2[ch][0] = make_float2(-expf(v.x) * kLog2e, -expf(v.y) * kLog2e);
+            A2[ch][1] = make_float2(-expf(v.z) * kLog2e, -expf(v.w) * kLog2e);
+        }
+        const float2 Dc = __ldg(reinterpret_cast<const float2 *>(p.D + c0) + ip);
+        const float2 bias = p.dt_bias ? __ldg(reinterpret_cast<const float2 *>(p.dt_bias + c0) + ip) : make_float2(0.f, 0.f);
+
+        // carry-in: the state our predecessor segment left behind
+        float *carry = cs.carry + ((size_t)b * p.ED + c0 + 2 * rp) * kNState + 4 * rq;
+        if (seg > 0) {
+            if (tid == 0) {
+                const int *f = cs.flags + (unit - per_seg);
+                while (ld_acquire(f) == 0) __nanosleep(100);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                const float4 v = __ldcg(reinterpret_cast<const float4 *>(carry + ch * kNState));
+                h[ch][0] = make_float2(v.x, v.y);
+                h[ch][1] = make_float2(v.z, v.w);
+            }
+        } else {
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) h[ch][0] = h[ch][1] = make_float2(0.f, 0.f);
+        }
+
+        float2 Du[4], gate[4];
+        auto phase_a = [&](int k) {   // per-(t, channel pair) scalars of chunk k -> shared slots; B|C rows -> fp32 quads
+            const int tb = t0 + k * kChunk;
+            const unsigned char *s = smem + (k % NST) * SM::kStage;
+            const T *sU = reinterpret_cast<const T *>(s);
+            const T *sD = reinterpret_cast<const T *>(s + SM::kTile);
+            const T *sZ = reinterpret_cast<const T *>(s + 2 * SM::kTile);
+            const T *sBr = reinterpret_cast<const T *>(s + NTILE * SM::kTile);   // B rows then C rows
+            float x[8], dl[8], sg[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 d2 = lds_pair(sD + (ir + 4 * i) * CPC, ip);
+                x[2 * i] = d2.x + bias.x;
+                x[2 * i + 1] = d2.y + bias.y;
+            }
+            if (sp) {
+                softplus_group<8, false>(x, dl, sg);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dl[i] = x[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int t = ir + 4 * i;
+                const bool valid = tb + t < t1;
+                const float2 u2 = lds_pair(sU + t * CPC, ip);
+                const float u0 = valid ? u2.x : 0.f, u1 = valid ? u2.y : 0.f;
+                const float dl0 = valid ? dl[2 * i] : 0.f, dl1 = valid ? dl[2 * i + 1] : 0.f;   // padded step: a = 1, bx = 0
+                sDD[t * (CPC / 2) + ip] = make_float4(dl0, dl0 * u0, dl1, dl1 * u1);
+                Du[i] = make_float2(Dc.x * u0, Dc.y * u1);
+                if (HAS_Z) {
+                    const float2 z2 = lds_pair(sZ + t * CPC, ip);
+                    gate[i] = make_float2(z2.x * sigmoid_fast(z2.x), z2.y * sigmoid_fast(z2.y));
+                }
+            }
+            {   // B|C rows -> fp32 quads: [t][B quads 0..3 | C quads 0..3]; 128 threads = 16 rows x 8 quads
+                const int t = tid >> 3, q8 = tid & 7;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (tb + t < t1) {
+                    const T *src = sBr + (q8 < 4 ? 0 : kChunk * 16) + t * 16 + 4 * (q8 & 3);
+                    const float2 lo = lds_pair(src, 0), hi = lds_pair(src, 1);
+                    v = make_float4(lo.x, lo.y, hi.x, hi.y);
+                }
+                sBC[tid] = v;
+            }
+        };
+
+        cp_async_wait<NST - 1>();
+        __syncthreads();
+        phase_a(0);
+
+        for (int k = 0; k < nch; ++k) {
+            const int tb = t0 + k * kChunk;
+            __syncthreads();   // (1) slots of chunk k are complete
+            {   // ---- the recurrence: 16 steps of this lane's 2 x 4 states ----
+#pragma unroll
+                for (int j = 0; j < kChunk; ++j) {
+                    if (j % kCkptV2 == 0 && ckq != nullptr && tb + j < t1) {   // states before step tb + j, for backward
+                        float4 *dst = ckq + (size_t)((tb + j) / kCkptV2) * ck_step;
+                        __stcs(dst, make_float4(h[0][0].x, h[0][0].y, h[0][1].x, h[0][1].y));
+                        __stcs(dst + kNState / 4, make_float4(h[1][0].x, h[1][0].y, h[1][1].x, h[1][1].y));
+                    }
+                    const float4 dd = dd_r[j * (CPC / 2)];
+                    const float4 B4 = bc_r[j * 8], C4 = bc_r[j * 8 + 4];
+                    const float2 B01 = make_float2(B4.x, B4.y), B23 = make_float2(B4.z, B4.w);
+                    const float2 C01 = make_float2(C4.x, C4.y), C23 = make_float2(C4.z, C4.w);
+                    float yv[2];
+#pragma unroll
+                    for (int ch = 0; ch < 2; ++ch) {
+                        const float dl = ch ? dd.z : dd.x, du = ch ? dd.w : dd.y;
+                        const float2 x0 = fmul2(splat2(dl), A2[ch][0]), x1 = fmul2(splat2(dl), A2[ch][1]);
+                        const float2 a0 = (ch == 0 && (j & 1)) ? ex2_poly2(x0) : ex2_2(x0);   // 2 of 8 exps per step pair... on the FMA pipe
+                        const float2 a1 = (ch == 1 && !(j & 1)) ? ex2_poly2(x1) : ex2_2(x1);
+                        h[ch][0] = ffma2(a0, h[ch][0], fmul2(splat2(du), B01));
+                        h[ch][1] = ffma2(a1, h[ch][1], fmul2(splat2(du), B23));
+                        const float2 y2 = ffma2(h[ch][1], C23, fmul2(h[ch][0], C01));
+                        yv[ch] = y2.x + y2.y;
+                    }
+                    y_w[j * (4 * kV4YPlane)] = make_float2(yv[0], yv[1]);
+                }
+            }
+            cp_async_wait<NST - 2>();   // chunk k + 1 has landed (this thread's pieces)
+            __syncthreads();            // (2) partial sums complete; chunk k + 1 visible; stage k % NST free
+            issue(k + NST);
+
+            // ---- per-(t, channel pair) epilogue of chunk k: sum the 4 quads, D skip, gate, store ----
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int t = ir + 4 * i;
+                if (tb + t < t1) {
+                    const float2 *yp = sY + (t * 4) * kV4YPlane + ip;
+                    const float2 p0 = yp[0], p1 = yp[kV4YPlane], p2 = yp[2 * kV4YPlane], p3 = yp[3 * kV4YPlane];
+                    float y0 = (p0.x + p1.x) + (p2.x + p3.x) + Du[i].x;
+                    float y1 = (p0.y + p1.y) + (p2.y + p3.y) + Du[i].y;
+                    if (yb != nullptr) stg_pair<T>(yb + (int64_t)(tb + t) * p.ED, y0, y1, true);
+                    if (HAS_Z) { y0 *= gate[i].x; y1 *= gate[i].y; }
+                    stg_pair<T>(ob + (int64_t)(tb + t) * p.o_rs, y0, y1, vec);
+                }
+            }
+            if (k + 1 < nch) phase_a(k + 1);
+        }
+
+        // carry-out / final state
+        if (seg == cs.nseg - 1) {
+            if (p.last_state != nullptr) {
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch)
+                    *(reinterpret_cast<float4 *>(p.last_state + ((size_t)b * p.ED + c0 + 2 * rp + ch) * kNState) + rq) =
+                        make_float4(h[ch][0].x, h[ch][0].y, h[ch][1].x, h[ch][1].y);
+            }
+        } else {
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch)
+                __stcg(reinterpret_cast<float4 *>(carry + ch * kNState), make_float4(h[ch][0].x, h[ch][0].y, h[ch][1].x, h[ch][1].y));
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) st_release(cs.flags + unit, 1);
+        }
+        cp_async_wait<0>();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- host
+template <typename T, bool HAS_Z, int CPB>
+static void launch_fwd_v4_inst(const ScanParams &p, const ChainSched &cs, cudaStream_t st) {
+    auto kernel = selscan_fwd_v4_kernel<T, HAS_Z, CPB>;
+    constexpr size_t smem = FwdV4Smem<T, HAS_Z>::kTotal;
+    static thread_local int cache_total = -1, cache_grid = 0;
+    if (cache_total != cs.total) {
+        int per_sm = 0;
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kV4NT, smem) != cudaSuccess || per_sm < 1) {
+            (void)cudaGetLastError();
+            per_sm = 1;
+        }
+        const int64_t slots = (int64_t)sm_count() * per_sm;
+        cache_grid = (int)(cs.total < slots ? cs.total : slots);
+        cache_total = cs.total;
+    }
+    kernel<<<cache_grid, kV4NT, smem, st>>>(p, cs);
+}
+
+// called by launch_fwd_v2_t when the channel block is 64 wide: same plan, same workspace, same checkpoints
+template <typename T>
+void v4_launch_fwd_kernel(const ScanParams &p, const ChainSched &cs, bool has_z, int cpb, cudaStream_t st) {
+    if (has_z) {
+        if (cpb == 16) launch_fwd_v4_inst<T, true, 16>(p, cs, st);
+        else launch_fwd_v4_inst<T, true, 0>(p, cs, st);
+    } else {
+        if (cpb == 16) launch_fwd_v4_inst<T, false, 16>(p, cs, st);
+        else launch_fwd_v4_inst<T, false, 0>(p, cs, st);
+    }
+}
+template void v4_launch_fwd_kernel<float>(const ScanParams &, const ChainSched &, bool, int, cudaStream_t);
+template void v4_launch_fwd_kernel<__nv_bfloat16>(const ScanParams &, const ChainSched &, bool, int, cudaStream_t);
+template void v4_launch_fwd_kernel<__half>(const ScanParams &, const ChainSched &, bool, int, cudaStream_t);
+
+}  // namespace gfe
