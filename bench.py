@@ -148,6 +148,8 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default=None, choices=[None, "f32", "bf16", "f16"])
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-rows", type=int, default=0, help="batch rows per pipeline chunk of the e2e leg (0 = B/8)")
+    ap.add_argument("--batch", type=int, default=0, help="override the workload's per-GPU batch (A/B measurements)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
     args = ap.parse_args()
@@ -156,6 +158,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     B, L, d_model, dts = WORKLOADS[args.workload]
+    B = args.batch or B
     dts = args.dtype or dts
     ED = 2 * d_model
     s_bytes = 4 if dts == "f32" else 2
@@ -287,29 +290,24 @@ def main():
                 "note": "selective scan at N=16 is MUFU/FP32-pipe co-limited on B200 (DESIGN.md, 'Why not 60 %')"}
     gpu_launches = int(sum(v[1] for v in kern.values()))
 
-    # ---- e2e: same step through the public API with HOST (pinned) buffers, copies inside the timed region
+    # ---- e2e: the same step through the public host-buffer API (gfe_mamba_b200.host_pipeline.HostScanPipeline): pinned HOST
+    #      inputs -> H2D, fused fwd+bwd, D2H of out and every activation gradient into pinned HOST outputs, all inside the
+    #      timed region; the pipeline overlaps the three over row chunks of the batch.
+    from gfe_mamba_b200.host_pipeline import HostScanPipeline
     d0 = sets[0]
     host_in = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in d0.items()}
     for k, v in d0.items():
         host_in[k].copy_(v.detach())
-    dev_in = {k: torch.empty_like(v.detach()) for k, v in d0.items()}
-    host_out = None
+    host_out = {k: torch.empty((B, L, N_STATE if k in ("dBm", "dCm") else ED), dtype=dt).pin_memory()
+                for k in ("out", "du", "ddelta", "dz", "dBm", "dCm")}
+    del sets, d0
+    torch.cuda.empty_cache()
+    pipe = HostScanPipeline(B, L, ED, N_STATE, dt, dev, rows_per_chunk=args.e2e_rows or None, has_z=True)
 
     def e2e_step():
-        nonlocal host_out
-        for k in dev_in:
-            dev_in[k].copy_(host_in[k], non_blocking=True)
-        leaves = {k: dev_in[k].requires_grad_() for k in ("u", "delta", "z", "Bm", "Cm")}
-        out = selective_scan_fn(leaves["u"], leaves["delta"], A_log, leaves["Bm"], leaves["Cm"], D, z=leaves["z"], dt_bias=bias)
-        grads = torch.autograd.grad(out, tuple(leaves.values()) + (A_log, D, bias), dev_in["dout"])
-        res = (out,) + grads
-        if host_out is None:
-            host_out = [torch.empty(r.shape, dtype=r.dtype).pin_memory() for r in res]
-        for h, r in zip(host_out, res):
-            h.copy_(r.detach(), non_blocking=True)
-        for k in leaves:
-            dev_in[k] = dev_in[k].detach()
+        g = pipe.run(host_in, A_log.detach(), D.detach(), bias.detach(), host_out)
         torch.cuda.current_stream().synchronize()
+        return g
 
     e2e_step()
     sync_all()
@@ -322,10 +320,9 @@ def main():
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    h2d = sum(v.numel() * v.element_size() for v in host_in.values())
-    d2h = sum(v.numel() * v.element_size() for v in host_out)
-    e2e = {"value": world * B * L / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "ms_per_step": round(e2e_s * 1e3, 3), "steps": args.e2e_steps}
+    e2e = {"value": world * B * L / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
+           "ms_per_step": round(e2e_s * 1e3, 3), "steps": args.e2e_steps, "rows_per_chunk": pipe.rows,
+           "api": "gfe_mamba_b200.host_pipeline.HostScanPipeline.run (pinned host in/out, H2D | fwd+bwd | D2H overlapped over row chunks)"}
 
     # ---- CPU baseline beside the GPU number (rank 0, N = 1 only)
     cpu = None

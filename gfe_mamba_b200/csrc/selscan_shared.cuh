@@ -196,6 +196,20 @@ __device__ __forceinline__ void stage_tile(unsigned char *dst, const T *src, int
         }
     }
 }
+// One 16-row tile whose 16 * ROW_ELEMS * sizeof(T) / 16 pieces are at most NT: every thread moves at most ONE 16-byte
+// piece, no loop, row stride taken from the (uniform) kernel parameters.  Falls back to stage_tile for plain loads.
+template <typename T, int CPB, int ROW_ELEMS, int NT>
+__device__ __forceinline__ void stage_tile1(unsigned char *dst, const T *src, int64_t rs, int nrows, int tid) {
+    constexpr int RB = ROW_ELEMS * (int)sizeof(T);
+    constexpr int PPR = RB / 16;
+    if constexpr (CPB == 16 && kChunk * PPR <= NT) {
+        const int row = tid / PPR, piece = tid % PPR;
+        if (tid < kChunk * PPR && row < nrows)
+            cp_async<16>(smem_u32(dst) + tid * 16, reinterpret_cast<const char *>(src + (int64_t)row * rs) + piece * 16);
+    } else {
+        stage_tile<T, CPB, ROW_ELEMS, NT>(dst, src, rs, nrows, tid);
+    }
+}
 #endif  // __CUDACC__
 
 // host side (selscan_v2_*.cu)

@@ -36,6 +36,12 @@ int v2_check_alignment(const gfe_selscan_args *a);
 // finalize kernels live in selscan.cu
 void launch_bwd_finalize(const gfe_selscan_args *a, ScanParams &p, cudaStream_t st, int &rc);
 
+#ifndef GFE_BWD_KEEP_A
+#define GFE_BWD_KEEP_A 0       // 1: keep exp(delta A) of the half chunk in registers (160 regs, 3 CTAs / SM); 0: recompute (4 CTAs / SM)
+#endif
+#ifndef GFE_BWD_MINB
+#define GFE_BWD_MINB (GFE_BWD_KEEP_A ? 3 : 4)
+#endif
 constexpr int kBwdCPC = 32;    // channels per CTA
 constexpr int kBwdNT = 128;    // 4 lanes per channel: lane (c, q) owns states 4q..4q+3 (two float2 pairs) of channel c
 constexpr int kBwdWarps = kBwdNT / 32;
@@ -47,7 +53,7 @@ constexpr int kBCPlane = kChunk * 8 + 4;    // float4 per B|C plane; the 64 B sk
 
 template <typename T, bool HAS_Z>
 struct BwdV2Smem {
-    static constexpr int kStages = sizeof(T) == 4 ? 2 : 3;
+    static constexpr int kStages = (sizeof(T) == 4 || !GFE_BWD_KEEP_A) ? 2 : 3;   // 2 stages keep 4 CTAs / SM within 227 KB
     static constexpr int kTile = kChunk * kBwdCPC * (int)sizeof(T);    // one of u, delta, dout, y, z
     static constexpr int kNTile = HAS_Z ? 5 : 3;
     static constexpr int kBCRaw = kChunk * kNState * (int)sizeof(T);    // one of B, C
@@ -61,7 +67,7 @@ struct BwdV2Smem {
 };
 
 template <typename T, bool HAS_Z, int CPB>
-__global__ void __launch_bounds__(kBwdNT, 3) selscan_bwd_v2_kernel(ScanParams p, ChainSched cs) {
+__global__ void __launch_bounds__(kBwdNT, GFE_BWD_MINB) selscan_bwd_v2_kernel(ScanParams p, ChainSched cs) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_unit;
     using SM = BwdV2Smem<T, HAS_Z>;
@@ -123,16 +129,16 @@ __global__ void __launch_bounds__(kBwdNT, 3) selscan_bwd_v2_kernel(ScanParams p,
                 const int tb = (klast - i) * kChunk;
                 const int nrows = min(kChunk, t1 - tb);
                 unsigned char *s = smem + (i % NST) * SM::kStage;
-                stage_tile<T, CPB, CPC, NT>(s, ub + (int64_t)tb * p.u_rs, p.u_rs, nrows, tid);
-                stage_tile<T, CPB, CPC, NT>(s + SM::kTile, db + (int64_t)tb * p.d_rs, p.d_rs, nrows, tid);
-                stage_tile<T, CPB, CPC, NT>(s + 2 * SM::kTile, gb + (int64_t)tb * p.do_rs, p.do_rs, nrows, tid);
+                stage_tile1<T, CPB, CPC, NT>(s, ub + (int64_t)tb * p.u_rs, p.u_rs, nrows, tid);
+                stage_tile1<T, CPB, CPC, NT>(s + SM::kTile, db + (int64_t)tb * p.d_rs, p.d_rs, nrows, tid);
+                stage_tile1<T, CPB, CPC, NT>(s + 2 * SM::kTile, gb + (int64_t)tb * p.do_rs, p.do_rs, nrows, tid);
                 if (HAS_Z) {
-                    stage_tile<T, CPB, CPC, NT>(s + 3 * SM::kTile, yb + (int64_t)tb * p.ED, p.ED, nrows, tid);
-                    stage_tile<T, CPB, CPC, NT>(s + 4 * SM::kTile, zb + (int64_t)tb * p.z_rs, p.z_rs, nrows, tid);
+                    stage_tile1<T, CPB, CPC, NT>(s + 3 * SM::kTile, yb + (int64_t)tb * p.ED, p.ED, nrows, tid);
+                    stage_tile1<T, CPB, CPC, NT>(s + 4 * SM::kTile, zb + (int64_t)tb * p.z_rs, p.z_rs, nrows, tid);
                 }
                 unsigned char *sb = s + SM::kNTile * SM::kTile;
-                stage_tile<T, CPB, kNState, NT>(sb, Bb + (int64_t)tb * p.B_rs, p.B_rs, nrows, tid);
-                stage_tile<T, CPB, kNState, NT>(sb + SM::kBCRaw, Cb + (int64_t)tb * p.C_rs, p.C_rs, nrows, tid);
+                stage_tile1<T, CPB, kNState, NT>(sb, Bb + (int64_t)tb * p.B_rs, p.B_rs, nrows, tid);
+                stage_tile1<T, CPB, kNState, NT>(sb + SM::kBCRaw, Cb + (int64_t)tb * p.C_rs, p.C_rs, nrows, tid);
             }
             cp_async_commit();
         };
@@ -249,7 +255,10 @@ __global__ void __launch_bounds__(kBwdNT, 3) selscan_bwd_v2_kernel(ScanParams p,
                 const float4 *bc_p = bc_r + jo * 8;
                 float2 *s_p = s_w + jo * (4 * kSPlane);
                 float *red_p = red_w + jo * kRedRow;
-                float2 a0[kCkptV2], a1[kCkptV2], h0[kCkptV2 + 1], h1[kCkptV2 + 1];
+#if GFE_BWD_KEEP_A
+                float2 a0[kCkptV2], a1[kCkptV2];
+#endif
+                float2 h0[kCkptV2 + 1], h1[kCkptV2 + 1];
                 {
                     const float4 ck = half ? ck_hi : ck_lo;
                     h0[0] = sw ? make_float2(ck.y, ck.x) : make_float2(ck.x, ck.y);
@@ -260,10 +269,12 @@ __global__ void __launch_bounds__(kBwdNT, 3) selscan_bwd_v2_kernel(ScanParams p,
                     const float2 dd = *reinterpret_cast<const float2 *>(dd_p + j * 16);   // {dl, dl*u}
                     const float4 B4 = bc_p[j * 8];
                     const float2 dl2 = splat2(dd.x), du2 = splat2(dd.y);   // scalar-broadcast operands (R.F32), no moves
-                    a0[j] = ex2_2(fmul2(dl2, A2[0]));
-                    a1[j] = ex2_2(fmul2(dl2, A2[1]));
-                    h0[j + 1] = ffma2(a0[j], h0[j], fmul2(du2, make_float2(B4.x, B4.y)));
-                    h1[j + 1] = ffma2(a1[j], h1[j], fmul2(du2, make_float2(B4.z, B4.w)));
+                    const float2 e0 = ex2_2(fmul2(dl2, A2[0])), e1 = ex2_2(fmul2(dl2, A2[1]));
+#if GFE_BWD_KEEP_A
+                    a0[j] = e0; a1[j] = e1;
+#endif
+                    h0[j + 1] = ffma2(e0, h0[j], fmul2(du2, make_float2(B4.x, B4.y)));
+                    h1[j + 1] = ffma2(e1, h1[j], fmul2(du2, make_float2(B4.z, B4.w)));
                 }
 #pragma unroll
                 for (int jb = kCkptV2 - 2; jb >= 0; jb -= 2) {
@@ -279,8 +290,13 @@ __global__ void __launch_bounds__(kBwdNT, 3) selscan_bwd_v2_kernel(ScanParams p,
                         const float2 dc0 = fmul2(dy2, h0[j + 1]), dc1 = fmul2(dy2, h1[j + 1]);   // dC_t[n] += dy h[t]
                         const float2 db0 = fmul2(gg0, du2), db1 = fmul2(gg1, du2);               // dB_t[n] += g delta u
                         const float2 sb = ffma2(gg1, make_float2(B4.z, B4.w), fmul2(gg0, make_float2(B4.x, B4.y)));   // sum_n g B
+#if GFE_BWD_KEEP_A
                         G[0] = fmul2(a0[j], gg0);                                                // a[t] g[t]
                         G[1] = fmul2(a1[j], gg1);
+#else   // the decay factors are re-derived (MUFU has slack in backward) instead of living in 32 registers
+                        G[0] = fmul2(ex2_2(fmul2(dl2, A2[0])), gg0);
+                        G[1] = fmul2(ex2_2(fmul2(dl2, A2[1])), gg1);
+#endif
                         const float2 w0 = fmul2(G[0], h0[j]), w1 = fmul2(G[1], h1[j]);           // (d a) a = g a h[t-1]
                         const float2 sa = ffma2(w1, A2[1], fmul2(w0, A2[0]));                    // sum_n (da a) A log2e
                         dA[0] = ffma2(w0, dl2, dA[0]);                                           // dA[c,n] += (da a) delta

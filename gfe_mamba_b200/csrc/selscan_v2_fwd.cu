@@ -252,6 +252,19 @@ static void chain_plan(int B, int L, int nblk, int ctas_per_sm, int &nseg, int &
 
 static int fwd_cpc(int ED) { return ED % 64 == 0 ? 64 : 32; }
 
+template <typename T>
+void v4_launch_fwd_kernel(const ScanParams &p, const ChainSched &cs, bool has_z, int cpb, cudaStream_t st);   // selscan_v4_fwd.cu
+template <typename T>
+bool v5_launch_fwd_kernel(const ScanParams &p, const ChainSched &cs, bool has_z, int cpb, cudaStream_t st);   // selscan_v5_fwd.cu
+static bool v5_enabled() {   // opt-in (GFE_SELSCAN_V5=1): measured 0.84 ms against 0.80 ms for v4 on cfg3 (profiles/r01_fwd_variants.txt)
+    const char *e = getenv("GFE_SELSCAN_V5");
+    return e != nullptr && e[0] == '1';
+}
+static bool v4_enabled() {   // GFE_SELSCAN_V4=0: A/B measurements against the v2 forward kernel
+    const char *e = getenv("GFE_SELSCAN_V4");
+    return e == nullptr || e[0] != '0';
+}
+
 void v2_fwd_plan(int B, int L, int ED, int &cpc, int &nblk, int &nseg, int &seg_len) {
     cpc = fwd_cpc(ED);
     nblk = ED / cpc;
@@ -259,13 +272,14 @@ void v2_fwd_plan(int B, int L, int ED, int &cpc, int &nblk, int &nseg, int &seg_
 }
 void v2_bwd_plan(int B, int L, int ED, int &nblk, int &nseg, int &seg_len) {
     nblk = ED / 32;
-    chain_plan(B, L, nblk, 3, nseg, seg_len);
+    chain_plan(B, L, nblk, 4, nseg, seg_len);
 }
 
 bool v2_applicable(int B, int L, int ED) {
     if (ED % 32 != 0) return false;
     if (const char *e = getenv("GFE_SELSCAN_V2")) {   // A/B measurements only
         if (e[0] == '0') return false;
+        if (e[0] == '1') return true;
     }
     return plan_segments(B, L, ED).nseg == 1;   // enough (row, channel) parallelism: no L-split recomputation needed
 }
@@ -417,7 +431,10 @@ static int launch_fwd_v2_t(const gfe_selscan_args *a, cudaStream_t st) {
     if (v2_pair_stores(a, false)) p.flags |= kFlagPairStores;
     ScopedKernelTimer tm(K_SELSCAN_FWD, st);
 #define GFE_V2F(HZ, CPB, CPC) launch_fwd_v2_inst<T, HZ, CPB, CPC>(p, cs, st)
-    if (cpc == 64) {
+    if (cpc == 64 && v4_enabled()) {
+        // two channels per lane: warp-specialised (selscan_v5_fwd.cu), else the single-role kernel (selscan_v4_fwd.cu)
+        if (!(v5_enabled() && v5_launch_fwd_kernel<T>(p, cs, hz, cpb, st))) v4_launch_fwd_kernel<T>(p, cs, hz, cpb, st);
+    } else if (cpc == 64) {
         if (hz && cpb == 16) GFE_V2F(true, 16, 64);
         else if (hz) GFE_V2F(true, 0, 64);
         else if (cpb == 16) GFE_V2F(false, 16, 64);

@@ -20,6 +20,12 @@ namespace gfe {
 
 constexpr int kV4CPC = 64;            // channels per CTA
 constexpr int kV4NT = 2 * kV4CPC;     // 128 threads: lane (pair, quad) owns 2 channels x 4 states
+#ifndef GFE_V4_POLY
+#define GFE_V4_POLY 2
+#endif
+#ifndef GFE_V4_MINB
+#define GFE_V4_MINB 3
+#endif
 constexpr int kV4YPlane = 36;         // float2 per (t, quad) plane of the partial C.h: 32 pairs + 32 B skew (conflict-free STS.64)
 
 template <typename T, bool HAS_Z>
@@ -36,7 +42,7 @@ struct FwdV4Smem {
 };
 
 template <typename T, bool HAS_Z, int CPB>
-__global__ void __launch_bounds__(kV4NT, 4) selscan_fwd_v4_kernel(ScanParams p, ChainSched cs) {
+__global__ void __launch_bounds__(kV4NT, GFE_V4_MINB) selscan_fwd_v4_kernel(ScanParams p, ChainSched cs) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_unit;
     using SM = FwdV4Smem<T, HAS_Z>;
@@ -241,8 +247,9 @@ __global__ void __launch_bounds__(kV4NT, 4) selscan_fwd_v4_kernel(ScanParams p, 
                     for (int ch = 0; ch < 2; ++ch) {
                         const float dl = ch ? dd.z : dd.x, du = ch ? dd.w : dd.y;
                         const float2 x0 = fmul2(splat2(dl), A2[ch][0]), x1 = fmul2(splat2(dl), A2[ch][1]);
-                        const float2 a0 = (ch == 0 && (j & 1)) ? ex2_poly2(x0) : ex2_2(x0);   // 2 of 8 exps per step pair... on the FMA pipe
-                        const float2 a1 = (ch == 1 && !(j & 1)) ? ex2_poly2(x1) : ex2_2(x1);
+                        // GFE_V4_POLY of every 8 exps of a step run as a polynomial on the FMA pipe instead of MUFU.EX2
+                        const float2 a0 = (GFE_V4_POLY >= 1 && ch == 0 && (j & 1)) ? ex2_poly2(x0) : ex2_2(x0);
+                        const float2 a1 = (GFE_V4_POLY >= 2 && ch == 1 && !(j & 1)) ? ex2_poly2(x1) : ex2_2(x1);
                         h[ch][0] = ffma2(a0, h[ch][0], fmul2(splat2(du), B01));
                         h[ch][1] = ffma2(a1, h[ch][1], fmul2(splat2(du), B23));
                         const float2 y2 = ffma2(h[ch][1], C23, fmul2(h[ch][0], C01));

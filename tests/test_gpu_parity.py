@@ -353,6 +353,31 @@ def test_cfg3_full_size_properties_bf16():
     assert relerr(out_s, out.float() * 2) < 1e-2
 
 
+@pytest.mark.parametrize("rows", [1, 2, 5])
+def test_host_pipeline_matches_oracle_and_direct_call(rows):
+    """Host-buffer entry point (pinned host in/out, H2D | fwd+bwd | D2H overlapped over row chunks): same numbers as the
+    oracle and, row for row, as the device-tensor call (the chunk's batch size may select another kernel variant, so the
+    comparison is to tolerance, not bitwise); parameter gradients are summed over the chunks."""
+    from gfe_mamba_b200.host_pipeline import HostScanPipeline
+    B, L, ED, N = 5, 70, 64, 16
+    d = make_scan_inputs(B, L, ED, seed=77)
+    host_in = {k: torch.from_numpy(d[s]).pin_memory() for k, s in
+               (("u", "u"), ("delta", "draw"), ("z", "z"), ("Bm", "Bm"), ("Cm", "Cm"), ("dout", "dout"))}
+    host_out = {k: torch.empty((B, L, N if k in ("dBm", "dCm") else ED)).pin_memory() for k in ("out", "du", "ddelta", "dz", "dBm", "dCm")}
+    A_log, D, bias = cuda(d["A_log"]), cuda(d["D"]), cuda(d["bias"])
+    pipe = HostScanPipeline(B, L, ED, N, torch.float32, torch.device("cuda"), rows_per_chunk=rows)
+    for _ in range(2):   # second run reuses the double buffers
+        dA_log, dD, dbias = pipe.run(host_in, A_log, D, bias, host_out)
+        torch.cuda.synchronize()
+    got = dict(out=host_out["out"], du=host_out["du"], ddelta=host_out["ddelta"], dz=host_out["dz"], dB=host_out["dBm"],
+               dC=host_out["dCm"], dA_log=dA_log, dD=dD, ddt_bias=dbias)
+    compare(got, oracle_fused(d, torch.float32), TOL[torch.float32])
+    direct = run_fused(d, torch.float32)
+    for k in ("out", "du", "ddelta", "dz", "dB", "dC"):
+        assert relerr(got[k], direct[k]) < 1e-5, k
+    assert pipe.h2d_bytes == 4 * (4 * B * L * ED + 2 * B * L * N) and pipe.d2h_bytes == 4 * (4 * B * L * ED + 2 * B * L * N)
+
+
 def test_error_behaviour():
     from gfe_mamba_b200 import selective_scan_fn, pscan
     with pytest.raises(RuntimeError, match="no CPU fallback"):
