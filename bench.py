@@ -56,6 +56,17 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(workload, kernel, B):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed `ncu --set full` capture
+    of this workload (profiles/traffic.json, written by tools/ncu_traffic.py); None when no capture exists for it."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            rec = json.load(f)[workload]
+        return int(rec["kernels"][kernel]) if rec.get("batch_per_gpu") == B else None
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -148,7 +159,7 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default=None, choices=[None, "f32", "bf16", "f16"])
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--e2e-rows", type=int, default=0, help="batch rows per pipeline chunk of the e2e leg (0 = B/8)")
+    ap.add_argument("--e2e-rows", type=int, default=0, help="batch rows per pipeline chunk of the e2e leg (0 = B/4)")
     ap.add_argument("--batch", type=int, default=0, help="override the workload's per-GPU batch (A/B measurements)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
@@ -283,7 +294,7 @@ def main():
     dom_alg = {"selscan_fwd": fwd_b, "selscan_bwd": bwd_b}.get(dom["kernel"], fwd_b + bwd_b)
     achieved = dom_alg / (dom["avg_ms"] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(achieved / peak, 4), "traffic": measured_traffic(args.workload, dom["kernel"], B), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_alg,
                 "step_achieved": round((fwd_b + bwd_b) / (ms_per_step * 1e-3) / 1e9, 1),
                 "step_frac": round((fwd_b + bwd_b) / (ms_per_step * 1e-3) / 1e9 / peak, 4),

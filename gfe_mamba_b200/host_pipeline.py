@@ -25,6 +25,22 @@ _IN_KEYS = ("u", "delta", "z", "Bm", "Cm", "dout")
 _OUT_KEYS = ("out", "du", "ddelta", "dz", "dBm", "dCm")
 
 
+def chunk_schedule(B: int, big: int):
+    """Rows per chunk: 1, 1, 2, 4, ... up to ``big``, flat in the middle, mirrored at the end.  The first copy-in and the
+    last copy-out are the only transfers nothing overlaps with, so they are kept one row long; the middle chunks are
+    large enough for the kernels to fill the GPU."""
+    up, r = [], 1
+    while r < big and sum(up) + r <= B // 4:
+        up.append(r)
+        if len(up) >= 2:
+            r *= 2
+    rest = B - 2 * sum(up)
+    mid = [big] * (rest // big) + ([rest % big] if rest % big else [])
+    sched = up + mid + up[::-1]
+    assert sum(sched) == B and all(0 < n <= big for n in sched), (B, big, sched)
+    return sched
+
+
 class HostScanPipeline:
     """Fused selective-scan forward + backward for HOST tensors of one fixed shape.
 
@@ -39,8 +55,9 @@ class HostScanPipeline:
         if not torch.cuda.is_available():
             raise RuntimeError("gfe_mamba_b200: HostScanPipeline needs a CUDA device (no CPU fallback)")
         self.B, self.L, self.ED, self.N, self.dtype, self.dev, self.has_z = B, L, ED, N, dtype, torch.device(device), has_z
-        self.rows = max(1, min(B, rows_per_chunk if rows_per_chunk else max(1, B // 8)))
-        self.nchunks = (B + self.rows - 1) // self.rows
+        self.rows = max(1, min(B, rows_per_chunk if rows_per_chunk else max(1, B // 4)))   # largest chunk (device buffers)
+        self.schedule = chunk_schedule(B, self.rows)
+        self.nchunks = len(self.schedule)
         self.s_in, self.s_comp, self.s_out = (torch.cuda.Stream(self.dev) for _ in range(3))
         shp = {"u": ED, "delta": ED, "z": ED, "dout": ED, "Bm": N, "Cm": N}
         keys = [k for k in _IN_KEYS if has_z or k != "z"]
@@ -59,9 +76,10 @@ class HostScanPipeline:
             s.wait_stream(cur)
         pacc = None
         keys = list(self.dev_in[0].keys())
-        for i in range(self.nchunks):
-            r0, r1 = i * self.rows, min(self.B, (i + 1) * self.rows)
-            n, slot = r1 - r0, i & 1
+        r1 = 0
+        for i, n in enumerate(self.schedule):
+            r0, r1 = r1, r1 + n
+            slot = i & 1
             with torch.cuda.stream(self.s_in):
                 if i >= 2:
                     self.s_in.wait_event(self.ev_free[slot])

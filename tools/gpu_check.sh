@@ -24,6 +24,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $OUT/launches_run.log 2>&1
 
 # full capture of the two dominant kernels (after the warm-up launches)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:selscan_.*_fast -s 6 -c 2 -f -o $OUT/prof_selscan \
+timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:selscan_(fwd_v4|bwd_v2)' -s 6 -c 2 -f -o $OUT/prof_selscan \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $OUT/prof_run.log 2>&1
+python tools/pcie_probe.py > $OUT/pcie.txt 2>&1; cat $OUT/pcie.txt
 ls -la $OUT
