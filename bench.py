@@ -150,7 +150,17 @@ def cpu_reference(B, L, ED, steps, warmup, budget_s):
 
 
 # ------------------------------------------------------------------------------------------------ main
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner at init), so the
+    real stdout is set aside for the JSON line and file descriptor 1 is pointed at stderr for everything else."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    out_stream = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -190,7 +200,7 @@ def main():
                 "cpu_baseline": {"value": r["tokens_per_s"], "unit": "tokens/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
                 "e2e": {"value": r["tokens_per_s"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        print(json.dumps(line), file=out_stream, flush=True)
         return
 
     import torch
@@ -347,7 +357,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": dts, "data": "synthetic", "config": cfg,
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
                 "kernels": kern_list}
-        print(json.dumps(line))
+        print(json.dumps(line), file=out_stream, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -136,6 +136,29 @@ __device__ __forceinline__ void softplus_group(const float (&x)[G], float (&dl)[
 }
 
 
+// Branch-free softplus of two values (no vote, no second formulation, so it can be interleaved with other work):
+// softplus(x) = max(x, 0) + log1p(w), w = exp(-|x|) in (0, 1], log1p(w) = 2 atanh(w / (2 + w)) with six odd terms
+// (s^2 <= 1/9: relative error < 1e-6 for every x; x > 20 returns x to fp32 rounding, the torch threshold).
+// Optionally sig = sigmoid(x) = d softplus / dx.
+template <bool WANT_SIG>
+__device__ __forceinline__ float2 softplus2(float2 x, float2 &sig) {
+    const float2 w = ex2_2(make_float2(fabsf(x.x) * -kLog2e, fabsf(x.y) * -kLog2e));
+    const float2 d = fadd2(w, splat2(2.0f));
+    const float2 s = fmul2(w, make_float2(rcp_approx(d.x), rcp_approx(d.y)));
+    const float2 s2 = fmul2(s, s);
+    float2 p = ffma2(s2, splat2(2.0f / 11.0f), splat2(2.0f / 9.0f));
+    p = ffma2(p, s2, splat2(2.0f / 7.0f));
+    p = ffma2(p, s2, splat2(2.0f / 5.0f));
+    p = ffma2(p, s2, splat2(2.0f / 3.0f));
+    p = ffma2(p, s2, splat2(2.0f));
+    const float2 r = fmul2(s, p);
+    if (WANT_SIG) {
+        const float2 q = make_float2(rcp_approx(1.0f + w.x), rcp_approx(1.0f + w.y));   // sigmoid(|x|)
+        sig = make_float2(x.x >= 0.f ? q.x : w.x * q.x, x.y >= 0.f ? q.y : w.y * q.y);
+    }
+    return make_float2(fmaxf(x.x, 0.f) + r.x, fmaxf(x.y, 0.f) + r.y);
+}
+
 // ---- chained-unit plumbing -----------------------------------------------------------------------------
 __device__ __forceinline__ int ld_acquire(const int *p) {
     int v;

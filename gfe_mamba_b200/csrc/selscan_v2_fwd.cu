@@ -260,6 +260,12 @@ static bool v5_enabled() {   // opt-in (GFE_SELSCAN_V5=1): measured 0.84 ms agai
     const char *e = getenv("GFE_SELSCAN_V5");
     return e != nullptr && e[0] == '1';
 }
+template <typename T>
+void v6_launch_fwd_kernel(const ScanParams &p, const ChainSched &cs, bool has_z, int cpb, cudaStream_t st);   // selscan_v6_fwd.cu
+static bool v6_enabled() {   // opt-in (GFE_SELSCAN_V6=1): measured 0.88 ms against 0.80 ms for v4 on cfg3 (profiles/r01_fwd_variants.txt)
+    const char *e = getenv("GFE_SELSCAN_V6");
+    return e != nullptr && e[0] == '1';
+}
 static bool v4_enabled() {   // GFE_SELSCAN_V4=0: A/B measurements against the v2 forward kernel
     const char *e = getenv("GFE_SELSCAN_V4");
     return e == nullptr || e[0] != '0';
@@ -433,7 +439,8 @@ static int launch_fwd_v2_t(const gfe_selscan_args *a, cudaStream_t st) {
 #define GFE_V2F(HZ, CPB, CPC) launch_fwd_v2_inst<T, HZ, CPB, CPC>(p, cs, st)
     if (cpc == 64 && v4_enabled()) {
         // two channels per lane: warp-specialised (selscan_v5_fwd.cu), else the single-role kernel (selscan_v4_fwd.cu)
-        if (!(v5_enabled() && v5_launch_fwd_kernel<T>(p, cs, hz, cpb, st))) v4_launch_fwd_kernel<T>(p, cs, hz, cpb, st);
+        if (v6_enabled() && (p.flags & kFlagPairStores)) v6_launch_fwd_kernel<T>(p, cs, hz, cpb, st);   // merged phases (selscan_v6_fwd.cu)
+        else if (!(v5_enabled() && v5_launch_fwd_kernel<T>(p, cs, hz, cpb, st))) v4_launch_fwd_kernel<T>(p, cs, hz, cpb, st);
     } else if (cpc == 64) {
         if (hz && cpb == 16) GFE_V2F(true, 16, 64);
         else if (hz) GFE_V2F(true, 0, 64);
