@@ -161,3 +161,27 @@ def test_product_never_imports_oracle():
                 if f.endswith((".py", ".cu", ".cuh", ".h")):
                     txt = open(os.path.join(dirpath, f)).read()
                     assert "oracle" not in txt.lower(), os.path.join(dirpath, f)
+
+
+def test_host_pipeline_chunk_schedule():
+    """Row chunks of the host-buffer pipeline: cover the batch exactly, never exceed the device buffers, and keep the
+    first copy-in / last copy-out (the only transfers nothing overlaps with) one row long when the batch allows it."""
+    from gfe_mamba_b200.host_pipeline import chunk_schedule
+    for B in (1, 2, 3, 5, 7, 16, 32, 100, 256):
+        for big in (1, 2, 3, 4, 8, 64):
+            if big > B:
+                continue
+            sched = chunk_schedule(B, big)
+            assert sum(sched) == B and all(1 <= n <= big for n in sched), (B, big, sched)
+            if B >= 8 and big >= 2:
+                assert sched[0] == 1 and sched[-1] == 1, (B, big, sched)
+    assert chunk_schedule(16, 4) == [1, 1, 2, 4, 4, 2, 1, 1]
+
+
+def test_host_pipeline_requires_cuda():
+    import torch
+    from gfe_mamba_b200.host_pipeline import HostScanPipeline
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        HostScanPipeline(2, 8, 32, 16, torch.float32, torch.device("cpu"))
