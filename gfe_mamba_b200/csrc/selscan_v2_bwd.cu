@@ -36,6 +36,9 @@ int v2_check_alignment(const gfe_selscan_args *a);
 // finalize kernels live in selscan.cu
 void launch_bwd_finalize(const gfe_selscan_args *a, ScanParams &p, cudaStream_t st, int &rc);
 
+#ifndef GFE_SOFTPLUS2
+#define GFE_SOFTPLUS2 0        // branch-free packed softplus: -2.8 % in the forward kernel, neutral here (and 3 registers over)
+#endif
 #ifndef GFE_BWD_KEEP_A
 #define GFE_BWD_KEEP_A 0       // 1: keep exp(delta A) of the half chunk in registers (160 regs, 3 CTAs / SM); 0: recompute (4 CTAs / SM)
 #endif
@@ -188,12 +191,24 @@ __global__ void __launch_bounds__(kBwdNT, GFE_BWD_MINB) selscan_bwd_v2_kernel(Sc
                 x[2 * ps] = d2.x + bias.x;
                 x[2 * ps + 1] = d2.y + bias.y;
             }
+#if GFE_SOFTPLUS2
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {   // branch-free packed softplus + sigmoid (selscan_shared.cuh)
+                float2 sg2;
+                const float2 v = softplus2<true>(make_float2(x[2 * j], x[2 * j + 1]), sg2);
+                dl[2 * j] = sp ? v.x : x[2 * j];
+                dl[2 * j + 1] = sp ? v.y : x[2 * j + 1];
+                sg[2 * j] = sp ? sg2.x : 1.0f;
+                sg[2 * j + 1] = sp ? sg2.y : 1.0f;
+            }
+#else
             if (sp) {
                 softplus_group<4, true>(x, dl, sg);
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { dl[j] = x[j]; sg[j] = 1.0f; }
             }
+#endif
 #pragma unroll
             for (int ps = 0; ps < 2; ++ps) {
                 const int t = ps * 8 + ir;

@@ -20,6 +20,9 @@ namespace gfe {
 
 constexpr int kV4CPC = 64;            // channels per CTA
 constexpr int kV4NT = 2 * kV4CPC;     // 128 threads: lane (pair, quad) owns 2 channels x 4 states
+#ifndef GFE_SOFTPLUS2
+#define GFE_SOFTPLUS2 1
+#endif
 #ifndef GFE_V4_POLY
 #define GFE_V4_POLY 2
 #endif
@@ -191,12 +194,23 @@ __global__ void __launch_bounds__(kV4NT, GFE_V4_MINB) selscan_fwd_v4_kernel(Scan
                 x[2 * i] = d2.x + bias.x;
                 x[2 * i + 1] = d2.y + bias.y;
             }
+#if GFE_SOFTPLUS2
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {   // branch-free packed softplus (selscan_shared.cuh)
+                float2 sg2;
+                const float2 v = softplus2<false>(make_float2(x[2 * i], x[2 * i + 1]), sg2);
+                dl[2 * i] = sp ? v.x : x[2 * i];
+                dl[2 * i + 1] = sp ? v.y : x[2 * i + 1];
+            }
+            (void)sg;
+#else
             if (sp) {
                 softplus_group<8, false>(x, dl, sg);
             } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) dl[i] = x[i];
             }
+#endif
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int t = ir + 4 * i;
