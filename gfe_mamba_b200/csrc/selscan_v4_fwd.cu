@@ -23,6 +23,9 @@ constexpr int kV4NT = 2 * kV4CPC;     // 128 threads: lane (pair, quad) owns 2 c
 #ifndef GFE_SOFTPLUS2
 #define GFE_SOFTPLUS2 1
 #endif
+#ifndef GFE_V4_PREFETCH
+#define GFE_V4_PREFETCH 1
+#endif
 #ifndef GFE_V4_POLY
 #define GFE_V4_POLY 2
 #endif
@@ -43,6 +46,51 @@ struct FwdV4Smem {
     static constexpr int kOffY = kOffBC + kChunk * 8 * 16;               // float2 [16][4][36] partial C.h of a channel pair
     static constexpr int kTotal = kOffY + kChunk * 4 * kV4YPlane * 8;
 };
+
+// The 16 recurrence steps of one chunk, with the slot loads software-pipelined by hand: neither nvcc nor ptxas moves the
+// three LDS of step j + 1 above the partial-sum STS of step j (may-alias shared addresses; __restrict__ does not reach
+// ptxas), so in source order every step waited out a full LDS latency before its first FMUL2 (seen in the SASS).
+__device__ __forceinline__ void v4_recur_chunk(const float4 *__restrict__ dd_r, const float4 *__restrict__ bc_r,
+                                               float2 *__restrict__ y_w, const float2 (&A2)[2][2], float2 (&h)[2][2],
+                                               float4 *__restrict__ ckq, size_t ck_step, int tb, int t1) {
+    constexpr int CPC = kV4CPC;
+    constexpr int PF = GFE_V4_PREFETCH;   // slot loads are issued PF steps ahead of their use, BEFORE the stores of the steps between
+    float4 dd_q[PF + 1], B_q[PF + 1], C_q[PF + 1];
+#pragma unroll
+    for (int i = 0; i < PF; ++i) { dd_q[i] = dd_r[i * (CPC / 2)]; B_q[i] = bc_r[i * 8]; C_q[i] = bc_r[i * 8 + 4]; }
+#pragma unroll
+    for (int j = 0; j < kChunk; ++j) {
+        if (j + PF < kChunk) {
+            dd_q[PF] = dd_r[(j + PF) * (CPC / 2)];
+            B_q[PF] = bc_r[(j + PF) * 8];
+            C_q[PF] = bc_r[(j + PF) * 8 + 4];
+        }
+        if (j % kCkptV2 == 0 && ckq != nullptr && tb + j < t1) {   // states before step tb + j, for backward
+            float4 *dst = ckq + (size_t)((tb + j) / kCkptV2) * ck_step;
+            __stcs(dst, make_float4(h[0][0].x, h[0][0].y, h[0][1].x, h[0][1].y));
+            __stcs(dst + kNState / 4, make_float4(h[1][0].x, h[1][0].y, h[1][1].x, h[1][1].y));
+        }
+        const float4 dd = dd_q[0], B4 = B_q[0], C4 = C_q[0];
+#pragma unroll
+        for (int i = 0; i < PF; ++i) { dd_q[i] = dd_q[i + 1]; B_q[i] = B_q[i + 1]; C_q[i] = C_q[i + 1]; }
+        const float2 B01 = make_float2(B4.x, B4.y), B23 = make_float2(B4.z, B4.w);
+        const float2 C01 = make_float2(C4.x, C4.y), C23 = make_float2(C4.z, C4.w);
+        float yv[2];
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            const float dl = ch ? dd.z : dd.x, du = ch ? dd.w : dd.y;
+            const float2 x0 = fmul2(splat2(dl), A2[ch][0]), x1 = fmul2(splat2(dl), A2[ch][1]);
+            // GFE_V4_POLY of every 8 exps of a step run as a polynomial on the FMA pipe instead of MUFU.EX2
+            const float2 a0 = (GFE_V4_POLY >= 1 && ch == 0 && (j & 1)) ? ex2_poly2(x0) : ex2_2(x0);
+            const float2 a1 = (GFE_V4_POLY >= 2 && ch == 1 && !(j & 1)) ? ex2_poly2(x1) : ex2_2(x1);
+            h[ch][0] = ffma2(a0, h[ch][0], fmul2(splat2(du), B01));
+            h[ch][1] = ffma2(a1, h[ch][1], fmul2(splat2(du), B23));
+            const float2 y2 = ffma2(h[ch][1], C23, fmul2(h[ch][0], C01));
+            yv[ch] = y2.x + y2.y;
+        }
+        y_w[j * (4 * kV4YPlane)] = make_float2(yv[0], yv[1]);
+    }
+}
 
 template <typename T, bool HAS_Z, int CPB>
 __global__ void __launch_bounds__(kV4NT, GFE_V4_MINB) selscan_fwd_v4_kernel(ScanParams p, ChainSched cs) {
@@ -244,34 +292,7 @@ __global__ void __launch_bounds__(kV4NT, GFE_V4_MINB) selscan_fwd_v4_kernel(Scan
         for (int k = 0; k < nch; ++k) {
             const int tb = t0 + k * kChunk;
             __syncthreads();   // (1) slots of chunk k are complete
-            {   // ---- the recurrence: 16 steps of this lane's 2 x 4 states ----
-#pragma unroll
-                for (int j = 0; j < kChunk; ++j) {
-                    if (j % kCkptV2 == 0 && ckq != nullptr && tb + j < t1) {   // states before step tb + j, for backward
-                        float4 *dst = ckq + (size_t)((tb + j) / kCkptV2) * ck_step;
-                        __stcs(dst, make_float4(h[0][0].x, h[0][0].y, h[0][1].x, h[0][1].y));
-                        __stcs(dst + kNState / 4, make_float4(h[1][0].x, h[1][0].y, h[1][1].x, h[1][1].y));
-                    }
-                    const float4 dd = dd_r[j * (CPC / 2)];
-                    const float4 B4 = bc_r[j * 8], C4 = bc_r[j * 8 + 4];
-                    const float2 B01 = make_float2(B4.x, B4.y), B23 = make_float2(B4.z, B4.w);
-                    const float2 C01 = make_float2(C4.x, C4.y), C23 = make_float2(C4.z, C4.w);
-                    float yv[2];
-#pragma unroll
-                    for (int ch = 0; ch < 2; ++ch) {
-                        const float dl = ch ? dd.z : dd.x, du = ch ? dd.w : dd.y;
-                        const float2 x0 = fmul2(splat2(dl), A2[ch][0]), x1 = fmul2(splat2(dl), A2[ch][1]);
-                        // GFE_V4_POLY of every 8 exps of a step run as a polynomial on the FMA pipe instead of MUFU.EX2
-                        const float2 a0 = (GFE_V4_POLY >= 1 && ch == 0 && (j & 1)) ? ex2_poly2(x0) : ex2_2(x0);
-                        const float2 a1 = (GFE_V4_POLY >= 2 && ch == 1 && !(j & 1)) ? ex2_poly2(x1) : ex2_2(x1);
-                        h[ch][0] = ffma2(a0, h[ch][0], fmul2(splat2(du), B01));
-                        h[ch][1] = ffma2(a1, h[ch][1], fmul2(splat2(du), B23));
-                        const float2 y2 = ffma2(h[ch][1], C23, fmul2(h[ch][0], C01));
-                        yv[ch] = y2.x + y2.y;
-                    }
-                    y_w[j * (4 * kV4YPlane)] = make_float2(yv[0], yv[1]);
-                }
-            }
+            v4_recur_chunk(dd_r, bc_r, y_w, A2, h, ckq, ck_step, tb, t1);   // 16 steps of this lane's 2 x 4 states
             cp_async_wait<NST - 2>();   // chunk k + 1 has landed (this thread's pieces)
             __syncthreads();            // (2) partial sums complete; chunk k + 1 visible; stage k % NST free
             issue(k + NST);
