@@ -39,6 +39,9 @@ void launch_bwd_finalize(const gfe_selscan_args *a, ScanParams &p, cudaStream_t 
 #ifndef GFE_SOFTPLUS2
 #define GFE_SOFTPLUS2 0        // branch-free packed softplus: -2.8 % in the forward kernel, neutral here (and 3 registers over)
 #endif
+#ifndef GFE_BWD_PREFETCH
+#define GFE_BWD_PREFETCH 1
+#endif
 #ifndef GFE_BWD_KEEP_A
 #define GFE_BWD_KEEP_A 0       // 1: keep exp(delta A) of the half chunk in registers (160 regs, 3 CTAs / SM); 0: recompute (4 CTAs / SM)
 #endif
@@ -291,14 +294,24 @@ __global__ void __launch_bounds__(kBwdNT, GFE_BWD_MINB) selscan_bwd_v2_kernel(Sc
                     h0[j + 1] = ffma2(e0, h0[j], fmul2(du2, make_float2(B4.x, B4.y)));
                     h1[j + 1] = ffma2(e1, h1[j], fmul2(du2, make_float2(B4.z, B4.w)));
                 }
+#if GFE_BWD_PREFETCH
+                // slot loads of step j - 1 are issued before the stores of step j: neither nvcc nor ptxas moves an LDS above
+                // a (may-alias) STS, so in plain source order every step waited out a full LDS latency (seen in the SASS)
+                float4 dd_n = dd_p[(kCkptV2 - 1) * 16], B_n = bc_p[(kCkptV2 - 1) * 8], C_n = bc_p[(kCkptV2 - 1) * 8 + 4];
+#endif
 #pragma unroll
                 for (int jb = kCkptV2 - 2; jb >= 0; jb -= 2) {
                     float v[16];   // [kind (dB, dC)][step in group (2)][state in quad (4)]
 #pragma unroll
                     for (int jj = 1; jj >= 0; --jj) {
                         const int j = jb + jj;
+#if GFE_BWD_PREFETCH
+                        const float4 dd = dd_n, B4 = B_n, C4 = C_n;   // {dl, dl*u, dy, 0}
+                        if (j > 0) { dd_n = dd_p[(j - 1) * 16]; B_n = bc_p[(j - 1) * 8]; C_n = bc_p[(j - 1) * 8 + 4]; }
+#else
                         const float4 dd = dd_p[j * 16];   // {dl, dl*u, dy, 0}
                         const float4 B4 = bc_p[j * 8], C4 = bc_p[j * 8 + 4];
+#endif
                         const float2 dl2 = splat2(dd.x), du2 = splat2(dd.y), dy2 = splat2(dd.z);
                         const float2 gg0 = ffma2(make_float2(C4.x, C4.y), dy2, G[0]);   // g[t] = C dy + a[t+1] g[t+1]
                         const float2 gg1 = ffma2(make_float2(C4.z, C4.w), dy2, G[1]);
