@@ -212,24 +212,44 @@ __global__ void __launch_bounds__(kBwdNT, GFE_BWD_MINB) selscan_bwd_v2_kernel(Sc
                 for (int j = 0; j < 4; ++j) { dl[j] = x[j]; sg[j] = 1.0f; }
             }
 #endif
+            float2 uq[2], gq[2], zq[2], yq[2];   // every load of the phase before its first store (an LDS is never moved above an STS)
+#pragma unroll
+            for (int ps = 0; ps < 2; ++ps) {
+                const int t = ps * 8 + ir;
+                uq[ps] = lds_pair(sU + t * CPC, ip);
+                gq[ps] = lds_pair(sDo + t * CPC, ip);
+                if (HAS_Z) {
+                    zq[ps] = lds_pair(sZ + t * CPC, ip);
+                    yq[ps] = lds_pair(sY + t * CPC, ip);
+                }
+            }
+            float4 bcv = make_float4(0.f, 0.f, 0.f, 0.f);
+            {
+                const int t = tid >> 3, q8 = tid & 7;
+                if (tb + t < t1) {
+                    const T *src = sBr + (q8 < 4 ? 0 : kChunk * 16) + t * 16 + 4 * (q8 & 3);
+                    const float2 lo = lds_pair(src, 0), hi = lds_pair(src, 1);
+                    bcv = make_float4(lo.x, lo.y, hi.x, hi.y);
+                }
+            }
 #pragma unroll
             for (int ps = 0; ps < 2; ++ps) {
                 const int t = ps * 8 + ir;
                 const bool valid = tb + t < t1;
-                const float2 u2 = lds_pair(sU + t * CPC, ip);
-                const float2 g2 = lds_pair(sDo + t * CPC, ip);
+                const float2 u2 = uq[ps];
+                const float2 g2 = gq[ps];
                 const float u0 = valid ? u2.x : 0.f, u1 = valid ? u2.y : 0.f;
                 const float do0 = valid ? g2.x : 0.f, do1 = valid ? g2.y : 0.f;
                 const float dl0 = valid ? dl[2 * ps] : 0.f, dl1 = valid ? dl[2 * ps + 1] : 0.f;
                 float dy0 = do0, dy1 = do1;
                 if (HAS_Z) {
-                    const float2 z2 = lds_pair(sZ + t * CPC, ip);
+                    const float2 z2 = zq[ps];
                     const float z0 = valid ? z2.x : 0.f, z1 = valid ? z2.y : 0.f;
                     const float sz0 = sigmoid_fast(z0), sz1 = sigmoid_fast(z1);
                     dy0 = do0 * (z0 * sz0);
                     dy1 = do1 * (z1 * sz1);
                     if (valid) {   // dz = dout * d silu(z)/dz * y needs nothing from the sweeps
-                        const float2 y2 = lds_pair(sY + t * CPC, ip);
+                        const float2 y2 = yq[ps];
                         const float f0 = do0 * sz0 * fmaf(z0, 1.0f - sz0, 1.0f), f1 = do1 * sz1 * fmaf(z1, 1.0f - sz1, 1.0f);
                         stg_pair<T>(dzb + (int64_t)(tb + t) * p.dz_rs, f0 * y2.x, f1 * y2.y, vec);
                     }
@@ -239,17 +259,9 @@ __global__ void __launch_bounds__(kBwdNT, GFE_BWD_MINB) selscan_bwd_v2_kernel(Sc
                 sDD[kDDPlane + t * 16 + ip] = make_float4(dl1, dlu1, dy1, 0.f);    // odd channel
                 sEpi4[t * 16 + ip] = make_float4(u0, sg[2 * ps], u1, sg[2 * ps + 1]);
             }
-            {   // B|C rows -> fp32 quads, natural and pair-swapped order: [sw][t][B quads 0..3 | C quads 0..3]
-                const int t = tid >> 3, q8 = tid & 7;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (tb + t < t1) {
-                    const T *src = sBr + (q8 < 4 ? 0 : kChunk * 16) + t * 16 + 4 * (q8 & 3);
-                    const float2 lo = lds_pair(src, 0), hi = lds_pair(src, 1);
-                    v = make_float4(lo.x, lo.y, hi.x, hi.y);
-                }
-                sBC[tid] = v;
-                sBC[kBCPlane + tid] = make_float4(v.y, v.x, v.w, v.z);
-            }
+            // B|C rows as fp32 quads, natural and pair-swapped order: [sw][t][B quads 0..3 | C quads 0..3]
+            sBC[tid] = bcv;
+            sBC[kBCPlane + tid] = make_float4(bcv.y, bcv.x, bcv.w, bcv.z);
         };
 
         cp_async_wait<NST - 1>();

@@ -259,30 +259,36 @@ __global__ void __launch_bounds__(kV4NT, GFE_V4_MINB) selscan_fwd_v4_kernel(Scan
                 for (int i = 0; i < 8; ++i) dl[i] = x[i];
             }
 #endif
+            float2 uq[4], zq[4];   // every load of the phase before its first store (an LDS is never moved above an STS)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                uq[i] = lds_pair(sU + (ir + 4 * i) * CPC, ip);
+                if (HAS_Z) zq[i] = lds_pair(sZ + (ir + 4 * i) * CPC, ip);
+            }
+            float4 bcv = make_float4(0.f, 0.f, 0.f, 0.f);
+            {   // B|C rows -> fp32 quads: [t][B quads 0..3 | C quads 0..3]; 128 threads = 16 rows x 8 quads
+                const int t = tid >> 3, q8 = tid & 7;
+                if (tb + t < t1) {
+                    const T *src = sBr + (q8 < 4 ? 0 : kChunk * 16) + t * 16 + 4 * (q8 & 3);
+                    const float2 lo = lds_pair(src, 0), hi = lds_pair(src, 1);
+                    bcv = make_float4(lo.x, lo.y, hi.x, hi.y);
+                }
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int t = ir + 4 * i;
                 const bool valid = tb + t < t1;
-                const float2 u2 = lds_pair(sU + t * CPC, ip);
+                const float2 u2 = uq[i];
                 const float u0 = valid ? u2.x : 0.f, u1 = valid ? u2.y : 0.f;
                 const float dl0 = valid ? dl[2 * i] : 0.f, dl1 = valid ? dl[2 * i + 1] : 0.f;   // padded step: a = 1, bx = 0
                 sDD[t * (CPC / 2) + ip] = make_float4(dl0, dl0 * u0, dl1, dl1 * u1);
                 Du[i] = make_float2(Dc.x * u0, Dc.y * u1);
                 if (HAS_Z) {
-                    const float2 z2 = lds_pair(sZ + t * CPC, ip);
+                    const float2 z2 = zq[i];
                     gate[i] = make_float2(z2.x * sigmoid_fast(z2.x), z2.y * sigmoid_fast(z2.y));
                 }
             }
-            {   // B|C rows -> fp32 quads: [t][B quads 0..3 | C quads 0..3]; 128 threads = 16 rows x 8 quads
-                const int t = tid >> 3, q8 = tid & 7;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (tb + t < t1) {
-                    const T *src = sBr + (q8 < 4 ? 0 : kChunk * 16) + t * 16 + 4 * (q8 & 3);
-                    const float2 lo = lds_pair(src, 0), hi = lds_pair(src, 1);
-                    v = make_float4(lo.x, lo.y, hi.x, hi.y);
-                }
-                sBC[tid] = v;
-            }
+            sBC[tid] = bcv;
         };
 
         cp_async_wait<NST - 1>();
