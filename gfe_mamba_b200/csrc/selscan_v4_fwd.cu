@@ -27,7 +27,7 @@ constexpr int kV4NT = 2 * kV4CPC;     // 128 threads: lane (pair, quad) owns 2 c
 #define GFE_V4_PREFETCH 1
 #endif
 #ifndef GFE_V4_POLY
-#define GFE_V4_POLY 2
+#define GFE_V4_POLY 1
 #endif
 #ifndef GFE_V4_MINB
 #define GFE_V4_MINB 3
