@@ -158,6 +158,52 @@ def test_selscan_half_precision(dtype):
     compare(run_fused(d, dtype), oracle_fused(d, dtype), TOL[dtype])
 
 
+# ---- the chained kernels (selscan_v4_fwd / selscan_v2_{fwd,bwd}): selected when B * ED / 32 >= 296 warps -----------------
+@pytest.mark.parametrize("B,L,ED", [(24, 203, 512),    # ragged L (not a multiple of 8 / 16), one segment
+                                    (20, 1000, 512),   # several chained L-segments, ragged last one
+                                    (24, 203, 480),    # ED % 64 == 32: v2 forward (32-channel blocks)
+                                    (40, 16, 256), (40, 1, 256), (40, 9, 256)])   # shorter than one chunk
+def test_selscan_chained_fp32_vs_oracle(B, L, ED):
+    d = make_scan_inputs(B, L, ED, seed=B + L + ED)
+    compare(run_fused(d, torch.float32), oracle_fused(d, torch.float32), TOL[torch.float32])
+
+
+@pytest.mark.parametrize("use_z,use_bias,softplus", [(False, True, True), (True, False, True), (True, True, False),
+                                                     (False, False, False)])
+def test_selscan_chained_variants(use_z, use_bias, softplus):
+    d = make_scan_inputs(20, 300, 512, seed=6)
+    if not softplus:
+        d["draw"] = np.abs(d["draw"]) * 0.2 + 1e-3
+        d["bias"] = np.abs(d["bias"]) * 0.01
+    compare(run_fused(d, torch.float32, use_z, use_bias, softplus),
+            oracle_fused(d, torch.float32, use_z, use_bias, softplus), TOL[torch.float32])
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_selscan_chained_half_precision(dtype):
+    d = make_scan_inputs(20, 523, 512, seed=12)
+    compare(run_fused(d, dtype), oracle_fused(d, dtype), TOL[dtype])
+
+
+def test_selscan_chained_strided_views_and_inference():
+    """Chained kernels on in-place views (u|z halves of one tensor, B/C slices of x_proj's output) and without checkpoints
+    (no grad): same output as with them."""
+    from gfe_mamba_b200 import selective_scan_fn
+    B, L, ED, N, R = 20, 200, 512, 16, 32
+    d = make_scan_inputs(B, L, ED, seed=22)
+    xz = torch.cat([cuda(d["u"]), cuda(d["z"])], dim=-1)
+    dbc = torch.cat([torch.zeros(B, L, R, device="cuda"), cuda(d["Bm"]), cuda(d["Cm"])], dim=-1)
+    u, z = xz[..., :ED], xz[..., ED:]
+    Bm, Cm = dbc[..., R:R + N], dbc[..., R + N:]
+    A_log, D, bias = cuda(d["A_log"]), cuda(d["D"]), cuda(d["bias"])
+    with torch.no_grad():
+        out = selective_scan_fn(u, cuda(d["draw"]), A_log, Bm, Cm, D, z=z, dt_bias=bias)
+    want = orc.selscan_seq_fwd(d["u"], d["draw"], d["A_log"], d["Bm"], d["Cm"], d["D"], z=d["z"], dt_bias=d["bias"])
+    assert relerr(out, want) < TOL[torch.float32]
+    got = run_fused(d, torch.float32)
+    assert relerr(out, got["out"]) < 1e-6
+
+
 def test_selscan_l_split_path():
     """Few channels, long L -> plan_segments() splits L; carries are combined from segment summaries."""
     d = make_scan_inputs(1, 4096, 64, seed=3)
