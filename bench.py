@@ -172,6 +172,7 @@ def main():
     ap.add_argument("--e2e-rows", type=int, default=0, help="batch rows per pipeline chunk of the e2e leg (0 = B/4)")
     ap.add_argument("--batch", type=int, default=0, help="override the workload's per-GPU batch (A/B measurements)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not bind the process to the GPU's NUMA node for the e2e leg")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
     args = ap.parse_args()
 
@@ -314,7 +315,9 @@ def main():
     # ---- e2e: the same step through the public host-buffer API (gfe_mamba_b200.host_pipeline.HostScanPipeline): pinned HOST
     #      inputs -> H2D, fused fwd+bwd, D2H of out and every activation gradient into pinned HOST outputs, all inside the
     #      timed region; the pipeline overlaps the three over row chunks of the batch.
-    from gfe_mamba_b200.host_pipeline import HostScanPipeline
+    from gfe_mamba_b200.host_pipeline import HostScanPipeline, bind_host_to_gpu_node
+    orig_affinity = os.sched_getaffinity(0)
+    numa_cpus = bind_host_to_gpu_node(dev) if not args.no_numa_bind else None   # pinned buffers below land on the GPU's node
     d0 = sets[0]
     host_in = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in d0.items()}
     for k, v in d0.items():
@@ -342,8 +345,10 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e = {"value": world * B * L / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
-           "ms_per_step": round(e2e_s * 1e3, 3), "steps": args.e2e_steps, "rows_per_chunk": pipe.rows,
+           "ms_per_step": round(e2e_s * 1e3, 3), "steps": args.e2e_steps, "rows_per_chunk": pipe.rows, "host_cpus": numa_cpus,
            "api": "gfe_mamba_b200.host_pipeline.HostScanPipeline.run (pinned host in/out, H2D | fwd+bwd | D2H overlapped over row chunks)"}
+
+    os.sched_setaffinity(0, orig_affinity)   # the CPU baseline below uses every host core again
 
     # ---- CPU baseline beside the GPU number (rank 0, N = 1 only)
     cpu = None

@@ -25,6 +25,35 @@ _IN_KEYS = ("u", "delta", "z", "Bm", "Cm", "dout")
 _OUT_KEYS = ("out", "du", "ddelta", "dz", "dBm", "dCm")
 
 
+def bind_host_to_gpu_node(device: torch.device) -> Optional[str]:
+    """Pin this process to the CPUs that are local to ``device``'s PCIe root (sysfs ``local_cpulist``) so that pinned host
+    buffers allocated afterwards are first-touched on the GPU's own NUMA node.  With one process per GPU this keeps eight
+    ranks from streaming their 1.6 GB per step through one memory controller.  Returns the CPU list, or None when the
+    topology cannot be read (nothing is changed then)."""
+    import os
+    try:
+        bus = torch.cuda.get_device_properties(device).pci_bus_id
+        dom = torch.cuda.get_device_properties(device).pci_domain_id
+        dev = torch.cuda.get_device_properties(device).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/local_cpulist"
+        with open(path) as f:
+            text = f.read().strip()
+        cpus = set()
+        for part in text.split(","):
+            if "-" in part:
+                lo, hi = part.split("-")
+                cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return text
+    except Exception:
+        return None
+
+
 def chunk_schedule(B: int, big: int):
     """Rows per chunk: 1, 1, 2, 4, ... up to ``big``, flat in the middle, mirrored at the end.  The first copy-in and the
     last copy-out are the only transfers nothing overlaps with, so they are kept one row long; the middle chunks are
