@@ -65,6 +65,9 @@ SIGNATURES = {
     "gfe_conv1d_step": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64] + [ctypes.c_int] * 4 + [c_vp]),
     "gfe_ssm_step": (ctypes.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp,
                                     c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_u32, ctypes.c_int, c_vp]),
+    "gfe_add_rmsnorm_fwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_float, ctypes.c_int, c_vp]),
+    "gfe_add_rmsnorm_bwd_workspace_bytes": (c_sz, [c_i64, ctypes.c_int]),
+    "gfe_add_rmsnorm_bwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_int, c_vp, c_sz, c_vp]),
     "gfe_timing_enable": (ctypes.c_int, [ctypes.c_int]),
     "gfe_timing_kernel_count": (ctypes.c_int, []),
     "gfe_timing_kernel_name": (ctypes.c_char_p, [ctypes.c_int]),

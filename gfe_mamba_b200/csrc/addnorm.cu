@@ -1,0 +1,311 @@
+// addnorm.cu -- fused residual add + RMSNorm, forward and backward.
+// Replaces, per layer, the residual add of ResidualBlock.forward (mamba.py:103: mixer(norm(x)) + x) fused with the NEXT
+// layer's RMSNorm (mamba.py:408-418: x * rsqrt(mean(x^2) + eps) * weight):
+//     resid = x (+ a)                      one pass over the residual stream instead of add kernel + pow + mean + ...
+//     y     = (resid * rstd) * w,  rstd = rsqrt(mean(resid^2) + eps)
+// Backward (dy from the mixer, dres = gradient already flowing down the residual stream):
+//     g = dy * w;  dx = dres + rstd * (g - resid * rstd^2 * mean(g * resid));  dw = sum_rows dy * resid * rstd.
+// HBM-bound: forward reads x, a and writes resid, y (4 D s bytes per row), backward reads resid, dy, dres and writes dx.
+// One warp per row, the row cached in registers (D <= 32 * 8 vectors of 16 bytes), 16-byte coalesced accesses, warp
+// shuffle reductions; dw is accumulated per lane over a grid-stride loop of rows, reduced per CTA in shared memory and
+// written as one partial row per CTA; a second tiny kernel adds the partial rows (deterministic, no atomics).
+#include "common.cuh"
+
+namespace gfe {
+
+constexpr int kNormWarps = 8;          // rows in flight per CTA
+constexpr int kNormMaxVec = 8;         // 16-byte vectors per lane held in registers
+
+template <typename T> struct Vec16 { static constexpr int n = 16 / (int)sizeof(T); };
+
+template <typename T>
+__device__ __forceinline__ void load16(const T *p, float (&v)[Vec16<T>::n]) {
+    const uint4 raw = *reinterpret_cast<const uint4 *>(p);
+    const T *e = reinterpret_cast<const T *>(&raw);
+#pragma unroll
+    for (int i = 0; i < Vec16<T>::n; ++i) v[i] = to_f(e[i]);
+}
+template <typename T>
+__device__ __forceinline__ void store16(T *p, const float (&v)[Vec16<T>::n]) {
+    uint4 raw;
+    T *e = reinterpret_cast<T *>(&raw);
+#pragma unroll
+    for (int i = 0; i < Vec16<T>::n; ++i) e[i] = from_f<T>(v[i]);
+    *reinterpret_cast<uint4 *>(p) = raw;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// NV = vectors per lane (compile-time), D == any multiple of the vector width with D <= 32 * NV * VEC
+template <typename T, int NV, bool HAS_A>
+__global__ void __launch_bounds__(32 * kNormWarps) add_rmsnorm_fwd_kernel(const T *__restrict__ x, const T *__restrict__ a,
+                                                                          const float *__restrict__ w, T *__restrict__ resid,
+                                                                          T *__restrict__ y, float *__restrict__ rstd_out,
+                                                                          int64_t rows, int D, float eps) {
+    constexpr int VEC = Vec16<T>::n;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nvec = D / VEC;
+    float wv[NV][VEC];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int v = lane + 32 * i;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) wv[i][e] = v < nvec ? __ldg(w + v * VEC + e) : 0.f;
+    }
+    for (int64_t r = (int64_t)blockIdx.x * kNormWarps + warp; r < rows; r += (int64_t)gridDim.x * kNormWarps) {
+        float xv[NV][VEC];
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int v = lane + 32 * i;
+            if (v < nvec) {
+                load16<T>(x + r * D + v * VEC, xv[i]);
+                if (HAS_A) {
+                    float av[VEC];
+                    load16<T>(a + r * D + v * VEC, av);
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) xv[i][e] = to_f(from_f<T>(xv[i][e] + av[e]));   // the stream is stored in T
+                    store16<T>(resid + r * D + v * VEC, xv[i]);
+                }
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) ss = fmaf(xv[i][e], xv[i][e], ss);
+            }
+        }
+        ss = warp_sum(ss);
+        const float rstd = rsqrtf(ss / (float)D + eps);
+        if (lane == 0 && rstd_out != nullptr) rstd_out[r] = rstd;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int v = lane + 32 * i;
+            if (v < nvec) {
+                float o[VEC];
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) o[e] = (xv[i][e] * rstd) * wv[i][e];   // the reference's order: (x * rstd) * w
+                store16<T>(y + r * D + v * VEC, o);
+            }
+        }
+    }
+}
+
+template <typename T, int NV, bool HAS_DRES>
+__global__ void __launch_bounds__(32 * kNormWarps) add_rmsnorm_bwd_kernel(const T *__restrict__ resid, const float *__restrict__ w,
+                                                                          const float *__restrict__ rstd_in, const T *__restrict__ dy,
+                                                                          const T *__restrict__ dres, T *__restrict__ dx,
+                                                                          float *__restrict__ dw_part, int64_t rows, int D) {
+    constexpr int VEC = Vec16<T>::n;
+    __shared__ float s_dw[kNormWarps][32 * VEC + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nvec = D / VEC;
+    float dwv[NV][VEC];   // w is re-read through the read-only path every row (L1 hit): registers go to x, g and dw
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) dwv[i][e] = 0.f;
+    for (int64_t r = (int64_t)blockIdx.x * kNormWarps + warp; r < rows; r += (int64_t)gridDim.x * kNormWarps) {
+        float xv[NV][VEC], gv[NV][VEC];
+        const float rstd = rstd_in[r];
+        float dot = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int v = lane + 32 * i;
+            if (v < nvec) {
+                load16<T>(resid + r * D + v * VEC, xv[i]);
+                load16<T>(dy + r * D + v * VEC, gv[i]);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    dwv[i][e] = fmaf(gv[i][e], xv[i][e] * rstd, dwv[i][e]);
+                    gv[i][e] *= __ldg(w + v * VEC + e);
+                    dot = fmaf(gv[i][e], xv[i][e], dot);
+                }
+            }
+        }
+        dot = warp_sum(dot);
+        const float c = dot / (float)D * rstd * rstd;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int v = lane + 32 * i;
+            if (v < nvec) {
+                float o[VEC];
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) o[e] = rstd * (gv[i][e] - xv[i][e] * c);
+                if (HAS_DRES) {
+                    float dv[VEC];
+                    load16<T>(dres + r * D + v * VEC, dv);
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) o[e] += dv[e];
+                }
+                store16<T>(dx + r * D + v * VEC, o);
+            }
+        }
+    }
+    // dw: add the CTA's warps, one partial row per CTA
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) s_dw[warp][lane * VEC + e] = dwv[i][e];
+        __syncthreads();
+        for (int j = threadIdx.x; j < 32 * VEC; j += 32 * kNormWarps) {
+            const int col = (32 * i) * VEC + j;   // vector (lane' + 32 i), element e -> column (lane' + 32 i) * VEC + e
+            if (col < D) {
+                float s = 0.f;
+#pragma unroll
+                for (int wq = 0; wq < kNormWarps; ++wq) s += s_dw[wq][j];
+                dw_part[(size_t)blockIdx.x * D + col] = s;
+            }
+        }
+    }
+}
+
+// block (32 columns, 8 slices of the partial rows): coalesced 128-byte reads, 8-way split of the serial sum
+__global__ void add_rmsnorm_dw_finalize_kernel(const float *__restrict__ part, float *__restrict__ dw, int nparts, int D) {
+    __shared__ float s_acc[8][33];
+    const int col = blockIdx.x * 32 + threadIdx.x;
+    float s = 0.f;
+    if (col < D)
+        for (int p = threadIdx.y; p < nparts; p += 8) s += part[(size_t)p * D + col];
+    s_acc[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && col < D) {
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t += s_acc[q][threadIdx.x];
+        dw[col] = t;
+    }
+}
+
+static int norm_grid(int64_t rows) {
+    const int64_t want = (rows + kNormWarps - 1) / kNormWarps;
+    const int64_t cap = (int64_t)sm_count() * 4;   // persistent: 4 CTAs of 8 warps per SM (fewer partial dw rows to add)
+    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+template <typename T>
+static int nv_for(int D) {
+    const int VEC = Vec16<T>::n;
+    if (D % VEC != 0) return 0;
+    const int nvec = D / VEC;
+    for (int nv : {1, 2, 3, 4, 6, 8})
+        if (nvec <= 32 * nv) return nv;
+    return 0;
+}
+
+template <typename T>
+static int launch_fwd_t(const void *x, const void *a, const float *w, void *resid, void *y, float *rstd, int64_t rows, int D,
+                        float eps, cudaStream_t st) {
+    const int nv = nv_for<T>(D);
+    if (nv == 0) {
+        set_error("add_rmsnorm: d_model=%d must be a multiple of %d and at most %d for this dtype", D, Vec16<T>::n, 256 * Vec16<T>::n);
+        return GFE_ERR_ARG;
+    }
+    const int grid = norm_grid(rows);
+    ScopedKernelTimer tm(K_ADDNORM_FWD, st);
+#define GFE_NF(NVv)                                                                                                          \
+    if (a) add_rmsnorm_fwd_kernel<T, NVv, true><<<grid, 32 * kNormWarps, 0, st>>>((const T *)x, (const T *)a, w, (T *)resid, (T *)y, rstd, rows, D, eps); \
+    else add_rmsnorm_fwd_kernel<T, NVv, false><<<grid, 32 * kNormWarps, 0, st>>>((const T *)x, nullptr, w, nullptr, (T *)y, rstd, rows, D, eps)
+    switch (nv) {
+        case 1: GFE_NF(1); break;
+        case 2: GFE_NF(2); break;
+        case 3: GFE_NF(3); break;
+        case 4: GFE_NF(4); break;
+        case 6: GFE_NF(6); break;
+        default: GFE_NF(8); break;
+    }
+#undef GFE_NF
+    return check_launch("add_rmsnorm_fwd");
+}
+
+template <typename T>
+static int launch_bwd_t(const void *resid, const float *w, const float *rstd, const void *dy, const void *dres, void *dx, float *dw,
+                        int64_t rows, int D, void *ws, size_t ws_bytes, cudaStream_t st) {
+    const int nv = nv_for<T>(D);
+    if (nv == 0) {
+        set_error("add_rmsnorm: d_model=%d must be a multiple of %d and at most %d for this dtype", D, Vec16<T>::n, 256 * Vec16<T>::n);
+        return GFE_ERR_ARG;
+    }
+    const int grid = norm_grid(rows);
+    const size_t need = (size_t)grid * D * sizeof(float);
+    if (ws == nullptr || ws_bytes < need) {
+        set_error("add_rmsnorm_bwd: workspace too small (%zu < %zu)", ws ? ws_bytes : (size_t)0, need);
+        return GFE_ERR_WORKSPACE;
+    }
+    float *part = reinterpret_cast<float *>(ws);
+    {
+        ScopedKernelTimer tm(K_ADDNORM_BWD, st);
+#define GFE_NB(NVv)                                                                                                          \
+    if (dres) add_rmsnorm_bwd_kernel<T, NVv, true><<<grid, 32 * kNormWarps, 0, st>>>((const T *)resid, w, rstd, (const T *)dy, (const T *)dres, (T *)dx, part, rows, D); \
+    else add_rmsnorm_bwd_kernel<T, NVv, false><<<grid, 32 * kNormWarps, 0, st>>>((const T *)resid, w, rstd, (const T *)dy, nullptr, (T *)dx, part, rows, D)
+        switch (nv) {
+            case 1: GFE_NB(1); break;
+            case 2: GFE_NB(2); break;
+            case 3: GFE_NB(3); break;
+            case 4: GFE_NB(4); break;
+            case 6: GFE_NB(6); break;
+            default: GFE_NB(8); break;
+        }
+#undef GFE_NB
+    }
+    int rc = check_launch("add_rmsnorm_bwd");
+    if (rc != GFE_OK) return rc;
+    {
+        ScopedKernelTimer tm(K_ADDNORM_BWD_FIN, st);
+        add_rmsnorm_dw_finalize_kernel<<<(D + 31) / 32, dim3(32, 8), 0, st>>>(part, dw, grid, D);
+    }
+    return check_launch("add_rmsnorm_dw_finalize");
+}
+
+}  // namespace gfe
+
+using namespace gfe;
+
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" {
+
+GFE_API size_t gfe_add_rmsnorm_bwd_workspace_bytes(int64_t rows, int D) {
+    return (size_t)norm_grid(rows) * (size_t)(D > 0 ? D : 0) * sizeof(float);
+}
+
+GFE_API int gfe_add_rmsnorm_fwd(const void *x, const void *a, const float *w, void *resid, void *y, float *rstd, int64_t rows,
+                                int D, float eps, int dtype, void *stream) {
+    if (x == nullptr || w == nullptr || y == nullptr || rows < 0 || D <= 0 || (a != nullptr && resid == nullptr)) {
+        set_error("add_rmsnorm_fwd: bad argument");
+        return GFE_ERR_ARG;
+    }
+    if (!aligned16(x) || !aligned16(a) || !aligned16(resid) || !aligned16(y)) {
+        set_error("add_rmsnorm_fwd: tensors must be 16-byte aligned and row-contiguous");
+        return GFE_ERR_ARG;
+    }
+    if (rows == 0) return GFE_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch (dtype) {
+        case GFE_F32: return launch_fwd_t<float>(x, a, w, resid, y, rstd, rows, D, eps, st);
+        case GFE_BF16: return launch_fwd_t<__nv_bfloat16>(x, a, w, resid, y, rstd, rows, D, eps, st);
+        case GFE_F16: return launch_fwd_t<__half>(x, a, w, resid, y, rstd, rows, D, eps, st);
+        default: set_error("add_rmsnorm_fwd: unsupported dtype %d", dtype); return GFE_ERR_DTYPE;
+    }
+}
+
+GFE_API int gfe_add_rmsnorm_bwd(const void *resid, const float *w, const float *rstd, const void *dy, const void *dres, void *dx,
+                                float *dw, int64_t rows, int D, int dtype, void *ws, size_t ws_bytes, void *stream) {
+    if (resid == nullptr || w == nullptr || rstd == nullptr || dy == nullptr || dx == nullptr || dw == nullptr || rows <= 0 || D <= 0) {
+        set_error("add_rmsnorm_bwd: bad argument");
+        return GFE_ERR_ARG;
+    }
+    if (!aligned16(resid) || !aligned16(dy) || !aligned16(dres) || !aligned16(dx)) {
+        set_error("add_rmsnorm_bwd: tensors must be 16-byte aligned and row-contiguous");
+        return GFE_ERR_ARG;
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch (dtype) {
+        case GFE_F32: return launch_bwd_t<float>(resid, w, rstd, dy, dres, dx, dw, rows, D, ws, ws_bytes, st);
+        case GFE_BF16: return launch_bwd_t<__nv_bfloat16>(resid, w, rstd, dy, dres, dx, dw, rows, D, ws, ws_bytes, st);
+        case GFE_F16: return launch_bwd_t<__half>(resid, w, rstd, dy, dres, dx, dw, rows, D, ws, ws_bytes, st);
+        default: set_error("add_rmsnorm_bwd: unsupported dtype %d", dtype); return GFE_ERR_DTYPE;
+    }
+}
+
+}  // extern "C"

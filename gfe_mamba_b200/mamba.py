@@ -2,9 +2,10 @@
 names/shapes (state-dict compatible) and call signatures; the work under ``MambaBlock`` is done by the
 sm_100a kernels behind ``gfe_mamba_b200.ops``.
 
-What stays in torch (by design): the four projections (cuBLAS GEMMs), RMSNorm and the residual add.
+What stays in torch (by design): the four projections (cuBLAS GEMMs).
 What moved into hand-written CUDA: causal depthwise conv + SiLU, softplus(+bias), discretisation, the scan,
-the C contraction, the D skip, the SiLU(z) gate, their backward passes, and the decode step.
+the C contraction, the D skip, the SiLU(z) gate, their backward passes, the decode step, and the
+residual add fused with the next layer's RMSNorm in ``Mamba.forward``.
 
 Reference line numbers below refer to cross_atten/mamba.py of Tinysqua/GFE-Mamba.
 """
@@ -17,7 +18,15 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
+from .ops import add_rmsnorm
 from .pscan import pscan
+
+
+def _fusable_norm(x: torch.Tensor, config) -> bool:
+    """The fused add + RMSNorm kernel handles 16-byte vector rows held in registers (ops.add_rmsnorm); anything else
+    takes the module-by-module path."""
+    vec = 16 // x.element_size()
+    return x.dtype in (torch.float32, torch.bfloat16, torch.float16) and config.d_model % vec == 0 and config.d_model <= 256 * vec
 
 
 @dataclass
@@ -62,9 +71,17 @@ class Mamba(nn.Module):
 
     def forward(self, x):
         # x : (B, L, D) -> (B, L, D)
+        if not (x.is_cuda and _fusable_norm(x, self.config)):
+            for layer in self.layers:
+                x = layer(x)
+            return x
+        # Same arithmetic as `x = mixer(norm(x)) + x` per layer (mamba.py:103), with every residual add fused into the
+        # NEXT layer's RMSNorm: one pass over the residual stream per layer instead of an add and a five-kernel norm.
+        resid, branch = x, None
         for layer in self.layers:
-            x = layer(x)
-        return x
+            resid, normed = add_rmsnorm(resid, branch, layer.norm.weight, layer.norm.eps)
+            branch = layer.mixer(normed)
+        return branch + resid
 
     def step(self, x, caches):
         # x : (B, D); caches : [(h, inputs)] per layer

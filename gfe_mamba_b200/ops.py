@@ -264,6 +264,62 @@ def causal_conv1d_silu(xin: torch.Tensor, weight: torch.Tensor, bias: Optional[t
     return _CausalConv1dSiluFn.apply(xin, weight, bias)
 
 
+# ----------------------------------------------------------------- residual add + RMSNorm
+class _AddRMSNormFn(torch.autograd.Function):
+    """resid = x (+ a);  y = (resid * rsqrt(mean(resid^2) + eps)) * w -- the residual add of ResidualBlock.forward
+    (cross_atten/mamba.py:103) fused with the next RMSNorm (mamba.py:408-418).  SURVEY 8f rank 1."""
+
+    @staticmethod
+    def forward(ctx, x, a, weight, eps: float):
+        dev = _require_cuda(x, a, weight)
+        if x.dtype not in _DT:
+            raise TypeError(f"add_rmsnorm: unsupported activation dtype {x.dtype}")
+        D = x.shape[-1]
+        if weight.shape != (D,) or (a is not None and a.shape != x.shape):
+            raise ValueError("add_rmsnorm: inconsistent shapes")
+        x_ = x.detach().contiguous()
+        a_ = None if a is None else a.detach().to(x.dtype).contiguous()
+        w_ = _f32(weight)
+        rows = x_.numel() // D
+        resid = torch.empty_like(x_) if a_ is not None else x_
+        y = torch.empty_like(x_)
+        need_grad = any(ctx.needs_input_grad)
+        rstd = torch.empty(rows, dtype=torch.float32, device=dev) if need_grad else None
+        l = nat.lib()
+        with torch.cuda.device(dev):
+            nat.check(l.gfe_add_rmsnorm_fwd(_ptr(x_), _ptr(a_), _ptr(w_), _ptr(resid if a_ is not None else None), _ptr(y),
+                                            _ptr(rstd), rows, D, float(eps), _DT[x.dtype], _stream(dev)), "add_rmsnorm_fwd")
+        if need_grad:
+            ctx.save_for_backward(resid, w_, rstd)
+            ctx.has_a = a is not None
+            ctx.wdtype = weight.dtype
+        return resid, y
+
+    @staticmethod
+    def backward(ctx, dresid, dy):
+        resid, w_, rstd = ctx.saved_tensors
+        dev = resid.device
+        D = resid.shape[-1]
+        rows = resid.numel() // D
+        dy_ = torch.zeros_like(resid) if dy is None else dy.detach().to(resid.dtype).contiguous()
+        dres_ = None if dresid is None else dresid.detach().to(resid.dtype).contiguous()
+        dx = torch.empty_like(resid)
+        dw = torch.empty(D, dtype=torch.float32, device=dev)
+        l = nat.lib()
+        with torch.cuda.device(dev):
+            nws = l.gfe_add_rmsnorm_bwd_workspace_bytes(rows, D)
+            ws = _bytes(nws, dev)
+            nat.check(l.gfe_add_rmsnorm_bwd(_ptr(resid), _ptr(w_), _ptr(rstd), _ptr(dy_), _ptr(dres_), _ptr(dx), _ptr(dw), rows, D,
+                                            _DT[resid.dtype], _ptr(ws), nws, _stream(dev)), "add_rmsnorm_bwd")
+        return dx, (dx if ctx.has_a else None), dw.to(ctx.wdtype), None
+
+
+def add_rmsnorm(x: torch.Tensor, a: Optional[torch.Tensor], weight: torch.Tensor, eps: float = 1e-5
+                ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Returns (resid, y): resid = x + a (or x itself when a is None), y = RMSNorm(resid) * weight.  x, a: (..., D)."""
+    return _AddRMSNormFn.apply(x, a, weight, eps)
+
+
 # ------------------------------------------------------------------------------- decode step
 @torch.no_grad()
 def conv1d_step(xin: torch.Tensor, inputs: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]

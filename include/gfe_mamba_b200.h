@@ -143,6 +143,21 @@ GFE_API int gfe_ssm_step(const void *u, int64_t u_bs, const void *delta, int64_t
                          const float *A_log, const float *D, const float *dt_bias, float *h,
                          void *out, int64_t out_bs, int B, int ED, int N, uint32_t flags, int dtype, void *stream);
 
+/* ------------------------------------------------- residual add + RMSNorm --
+ * the residual add of ResidualBlock.forward (mamba.py:103) fused with the next layer's RMSNorm
+ * (mamba.py:408-418).  Row-contiguous (rows, D) tensors in the activation dtype, 16-byte aligned; w: (D) fp32.
+ *   fwd: resid = x + a (a, resid may be NULL: plain RMSNorm of x);  y = (resid * rstd) * w,
+ *        rstd[r] = rsqrt(mean(resid[r]^2) + eps)  (fp32, saved for backward; may be NULL for inference)
+ *   bwd: dx = dres + d/dresid of the norm (dres may be NULL);  dw[j] = sum_r dy[r,j] * resid[r,j] * rstd[r]
+ * D must be a multiple of 16 / sizeof(element) and at most 256 * 16 / sizeof(element).
+ */
+GFE_API int gfe_add_rmsnorm_fwd(const void *x, const void *a, const float *w, void *resid, void *y, float *rstd,
+                                int64_t rows, int D, float eps, int dtype, void *stream);
+GFE_API size_t gfe_add_rmsnorm_bwd_workspace_bytes(int64_t rows, int D);
+GFE_API int gfe_add_rmsnorm_bwd(const void *resid, const float *w, const float *rstd, const void *dy, const void *dres,
+                                void *dx, float *dw, int64_t rows, int D, int dtype, void *ws, size_t ws_bytes,
+                                void *stream);
+
 /* -------------------------------------------------------- instrumentation --
  * Optional per-kernel device timing: when enabled, every kernel the library launches is bracketed by a
  * cudaEvent pair on the launching stream.  gfe_timing_collect() synchronises those events, adds the elapsed

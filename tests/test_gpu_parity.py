@@ -484,6 +484,55 @@ def test_host_pipeline_matches_oracle_and_direct_call(rows):
     assert pipe.h2d_bytes == 4 * (4 * B * L * ED + 2 * B * L * N) and pipe.d2h_bytes == 4 * (4 * B * L * ED + 2 * B * L * N)
 
 
+# ------------------------------------------------------------------------------- residual add + RMSNorm
+@pytest.mark.parametrize("rows,D,dtype", [(7, 128, torch.float32), (300, 768, torch.float32), (1000, 256, torch.bfloat16),
+                                          (33, 1024, torch.float32), (65, 2048, torch.bfloat16), (5, 512, torch.float16),
+                                          (1, 4, torch.float32)])
+@pytest.mark.parametrize("with_add", [True, False])
+def test_add_rmsnorm_vs_torch(rows, D, dtype, with_add):
+    """resid = x + a; y = x * rsqrt(mean(x^2) + eps) * w exactly as cross_atten/mamba.py:103 and :408-418, forward and backward
+    (dx, da, dw), against the same expression in torch fp64 on the inputs as the kernel sees them."""
+    from gfe_mamba_b200 import add_rmsnorm
+    g = torch.Generator(device="cpu").manual_seed(rows * 7 + D)
+    x = torch.randn(rows, D, generator=g).to(dtype).cuda().requires_grad_()
+    a = torch.randn(rows, D, generator=g).to(dtype).cuda().requires_grad_() if with_add else None
+    w = (1 + 0.1 * torch.randn(D, generator=g)).cuda().requires_grad_()
+    dres, dy = torch.randn(rows, D, generator=g).to(dtype).cuda(), torch.randn(rows, D, generator=g).to(dtype).cuda()
+    resid, y = add_rmsnorm(x, a, w, 1e-5)
+    (resid.float() * dres.float()).sum().add((y.float() * dy.float()).sum()).backward()
+    xd = x.detach().double().requires_grad_()
+    ad = a.detach().double().requires_grad_() if with_add else None
+    wd = w.detach().double().requires_grad_()
+    rd = (xd + ad).detach().to(dtype).double() + ((xd + ad) - (xd + ad).detach()) if with_add else xd   # value rounded to dtype, gradient of the sum
+    yd = rd * torch.rsqrt(rd.pow(2).mean(-1, keepdim=True) + 1e-5) * wd
+    ((rd * dres.double()).sum() + (yd * dy.double()).sum()).backward()
+    tol = TOL[dtype]
+    assert relerr(resid, rd.detach()) < tol and relerr(y, yd.detach()) < tol
+    assert relerr(x.grad, xd.grad) < tol and relerr(w.grad, wd.grad) < tol
+    if with_add:
+        assert relerr(a.grad, ad.grad) < tol
+
+
+def test_mamba_stack_fused_norm_matches_layerwise():
+    """Mamba.forward with the residual adds fused into the next RMSNorm == the reference's layer-by-layer formulation."""
+    from gfe_mamba_b200 import Mamba, MambaConfig
+    torch.manual_seed(3)
+    model = Mamba(MambaConfig(d_model=64, n_layers=3)).cuda()
+    x = torch.randn(2, 50, 64, device="cuda", requires_grad=True)
+    y = model(x)
+    y.square().mean().backward()
+    gx = x.grad.clone()
+    gp = {n: p.grad.clone() for n, p in model.named_parameters()}
+    model.zero_grad(); x.grad = None
+    h = x
+    for layer in model.layers:          # ResidualBlock.forward: mixer(norm(x)) + x with the torch RMSNorm module
+        h = layer(h)
+    h.square().mean().backward()
+    assert relerr(y, h) < 1e-5 and relerr(gx, x.grad) < 1e-4
+    for n, p in model.named_parameters():
+        assert relerr(gp[n], p.grad) < 1e-4, n
+
+
 def test_error_behaviour():
     from gfe_mamba_b200 import selective_scan_fn, pscan
     with pytest.raises(RuntimeError, match="no CPU fallback"):
