@@ -106,8 +106,16 @@ __global__ void __launch_bounds__(32 * kNormWarps) add_rmsnorm_bwd_kernel(const 
         for (int e = 0; e < VEC; ++e) dwv[i][e] = 0.f;
     for (int64_t r = (int64_t)blockIdx.x * kNormWarps + warp; r < rows; r += (int64_t)gridDim.x * kNormWarps) {
         float xv[NV][VEC], gv[NV][VEC];
+        uint4 dv_raw[HAS_DRES ? NV : 1];   // the third stream is requested together with the other two (kept packed)
         const float rstd = rstd_in[r];
         float dot = 0.f;
+        if (HAS_DRES) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int v = lane + 32 * i;
+                if (v < nvec) dv_raw[i] = *reinterpret_cast<const uint4 *>(dres + r * D + v * VEC);
+            }
+        }
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const int v = lane + 32 * i;
@@ -132,10 +140,9 @@ __global__ void __launch_bounds__(32 * kNormWarps) add_rmsnorm_bwd_kernel(const 
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) o[e] = rstd * (gv[i][e] - xv[i][e] * c);
                 if (HAS_DRES) {
-                    float dv[VEC];
-                    load16<T>(dres + r * D + v * VEC, dv);
+                    const T *dv = reinterpret_cast<const T *>(&dv_raw[i]);
 #pragma unroll
-                    for (int e = 0; e < VEC; ++e) o[e] += dv[e];
+                    for (int e = 0; e < VEC; ++e) o[e] += to_f(dv[e]);
                 }
                 store16<T>(dx + r * D + v * VEC, o);
             }
