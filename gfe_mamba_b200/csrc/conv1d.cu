@@ -3,7 +3,8 @@
 // Replaces nn.Conv1d(groups=ED, kernel_size=K, padding=K-1)(x.transpose(1,2))[:, :, :L].transpose(1,2)
 // followed by F.silu (cross_atten/mamba.py:128-131, 208-212): no transposes, the strided x half of
 // in_proj's output is read in place, the K-wide window slides through registers so every input element
-// is loaded once per time tile (+ K-1 halo).  lane = channel -> coalesced 64/128-byte rows.
+// is loaded once per time tile (+ K-1 halo).  A lane owns 4 (16-bit) / 2 (fp32) adjacent channels and moves them with
+// one 8-byte access, so a warp request covers 256 contiguous bytes of a row.
 //   forward : read xin, write u                      (2 * ED * s bytes / token)
 //   backward: read xin, du, write dxin               (3 * ED * s bytes / token), dw/dbias via
 //             per-(b, tile) partial sums + a deterministic finalize kernel.
@@ -11,7 +12,7 @@
 
 namespace gfe {
 
-constexpr int kConvTile = 64;   // time steps per thread
+constexpr int kConvTile = 128;  // time steps per thread (one partial dw|dbias row per tile)
 
 struct ConvParams {
     const void *xin, *du;
@@ -22,144 +23,212 @@ struct ConvParams {
     int B, L, ED, ntiles;
 };
 
-template <typename T, int K>
+// V adjacent channels per lane, moved as ONE load / store of V * sizeof(T) bytes (8 bytes when the layout allows it: 4
+// channels for 16-bit activations, 2 for fp32), so a warp request covers 256 contiguous bytes instead of 64 / 128.
+template <int BYTES> struct RawBytes;
+template <> struct RawBytes<2> { using type = unsigned short; };
+template <> struct RawBytes<4> { using type = unsigned int; };
+template <> struct RawBytes<8> { using type = uint2; };
+template <typename T, int V> struct ChanVec {
+    using Raw = typename RawBytes<V * (int)sizeof(T)>::type;
+    Raw raw;
+    __device__ __forceinline__ float get(int i) const { return to_f(reinterpret_cast<const T *>(&raw)[i]); }
+    __device__ __forceinline__ void set(int i, float v) { reinterpret_cast<T *>(&raw)[i] = from_f<T>(v); }
+    __device__ __forceinline__ static ChanVec load(const T *p) { ChanVec r; r.raw = __ldcs(reinterpret_cast<const Raw *>(p)); return r; }
+    __device__ __forceinline__ void store(T *p) const { __stcs(reinterpret_cast<Raw *>(p), raw); }
+};
+
+template <typename T, int K, int V>
 __global__ void __launch_bounds__(128) conv1d_silu_fwd_kernel(ConvParams p) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) * V;
     if (c >= p.ED) return;
     const int tile = blockIdx.y, b = blockIdx.z;
     const int t0 = tile * kConvTile, t1 = min(p.L, t0 + kConvTile);
     const T *x = reinterpret_cast<const T *>(p.xin) + (int64_t)b * p.x_bs + c;
     T *u = reinterpret_cast<T *>(p.u) + (int64_t)b * p.u_bs + c;
-    float w[K];
+    float w[V][K], bias[V];
 #pragma unroll
-    for (int k = 0; k < K; ++k) w[k] = __ldg(p.w + (size_t)c * K + k);
-    const float bias = p.bias ? __ldg(p.bias + c) : 0.f;
-
-    float win[K];   // win[k] = xin[t - (K-1) + k]
+    for (int i = 0; i < V; ++i) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) w[i][k] = __ldg(p.w + (size_t)(c + i) * K + k);
+        bias[i] = p.bias ? __ldg(p.bias + c + i) : 0.f;
+    }
+    float win[V][K];   // win[.][k] = xin[t - (K-1) + k]
 #pragma unroll
     for (int k = 0; k < K - 1; ++k) {
         const int t = t0 - (K - 1) + k;
-        win[k + 1] = t >= 0 ? to_f(ld_stream(x + (int64_t)t * p.x_rs)) : 0.f;
+        ChanVec<T, V> xv{};
+        if (t >= 0) xv = ChanVec<T, V>::load(x + (int64_t)t * p.x_rs);
+#pragma unroll
+        for (int i = 0; i < V; ++i) win[i][k + 1] = t >= 0 ? xv.get(i) : 0.f;
     }
     constexpr int U = 8;
     for (int tb = t0; tb < t1; tb += U) {
-        T xr[U];
+        ChanVec<T, V> xr[U];
 #pragma unroll
-        for (int j = 0; j < U; ++j) xr[j] = ld_stream(x + (int64_t)min(tb + j, t1 - 1) * p.x_rs);
+        for (int j = 0; j < U; ++j) xr[j] = ChanVec<T, V>::load(x + (int64_t)min(tb + j, t1 - 1) * p.x_rs);
 #pragma unroll
         for (int j = 0; j < U; ++j) {
             if (tb + j < t1) {
+                ChanVec<T, V> o;
 #pragma unroll
-                for (int k = 0; k < K - 1; ++k) win[k] = win[k + 1];
-                win[K - 1] = to_f(xr[j]);
-                float v = bias;
+                for (int i = 0; i < V; ++i) {
 #pragma unroll
-                for (int k = 0; k < K; ++k) v = fmaf(w[k], win[k], v);
-                st_stream(u + (int64_t)(tb + j) * p.u_rs, from_f<T>(v * sigmoid_fast(v)));
+                    for (int k = 0; k < K - 1; ++k) win[i][k] = win[i][k + 1];
+                    win[i][K - 1] = xr[j].get(i);
+                    float v = bias[i];
+#pragma unroll
+                    for (int k = 0; k < K; ++k) v = fmaf(w[i][k], win[i][k], v);
+                    o.set(i, v * sigmoid_fast(v));
+                }
+                o.store(u + (int64_t)(tb + j) * p.u_rs);
             }
         }
     }
 }
 
-template <typename T, int K>
+template <typename T, int K, int V>
 __global__ void __launch_bounds__(128) conv1d_silu_bwd_kernel(ConvParams p) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) * V;
     if (c >= p.ED) return;
     const int tile = blockIdx.y, b = blockIdx.z;
     const int t0 = tile * kConvTile, t1 = min(p.L, t0 + kConvTile);
     const T *x = reinterpret_cast<const T *>(p.xin) + (int64_t)b * p.x_bs + c;
     const T *du = reinterpret_cast<const T *>(p.du) + (int64_t)b * p.du_bs + c;
     T *dx = reinterpret_cast<T *>(p.dxin) + (int64_t)b * p.dx_bs + c;
-    float w[K];
+    float w[V][K], bias[V];
 #pragma unroll
-    for (int k = 0; k < K; ++k) w[k] = __ldg(p.w + (size_t)c * K + k);
-    const float bias = p.bias ? __ldg(p.bias + c) : 0.f;
-
-    float win[K], dvw[K], dw[K], db = 0.f;   // dvw[k] = dv[t - (K-1) + k]
+    for (int i = 0; i < V; ++i) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) { dvw[k] = 0.f; dw[k] = 0.f; }
+        for (int k = 0; k < K; ++k) w[i][k] = __ldg(p.w + (size_t)(c + i) * K + k);
+        bias[i] = p.bias ? __ldg(p.bias + c + i) : 0.f;
+    }
+    float win[V][K], dvw[V][K], dw[V][K], db[V];   // dvw[.][k] = dv[t - (K-1) + k]
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        db[i] = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) { dvw[i][k] = 0.f; dw[i][k] = 0.f; }
+    }
 #pragma unroll
     for (int k = 0; k < K - 1; ++k) {
         const int t = t0 - (K - 1) + k;
-        win[k + 1] = t >= 0 ? to_f(ld_stream(x + (int64_t)t * p.x_rs)) : 0.f;
+        ChanVec<T, V> xv{};
+        if (t >= 0) xv = ChanVec<T, V>::load(x + (int64_t)t * p.x_rs);
+#pragma unroll
+        for (int i = 0; i < V; ++i) win[i][k + 1] = t >= 0 ? xv.get(i) : 0.f;
     }
     // dv is needed K-1 steps past the tile to finish dxin of the tile's last steps
     const int tend = t1 + (K - 1);
     constexpr int U = 8;
     for (int tb = t0; tb < tend; tb += U) {
-        T xr[U], gr[U];
+        ChanVec<T, V> xr[U], gr[U];
 #pragma unroll
         for (int j = 0; j < U; ++j) {
             const int t = min(tb + j, p.L - 1);
-            xr[j] = ld_stream(x + (int64_t)t * p.x_rs);
-            gr[j] = ld_stream(du + (int64_t)t * p.du_rs);
+            xr[j] = ChanVec<T, V>::load(x + (int64_t)t * p.x_rs);
+            gr[j] = ChanVec<T, V>::load(du + (int64_t)t * p.du_rs);
         }
 #pragma unroll
         for (int j = 0; j < U; ++j) {
             const int t = tb + j;
             if (t < tend) {
-#pragma unroll
-                for (int k = 0; k < K - 1; ++k) { win[k] = win[k + 1]; dvw[k] = dvw[k + 1]; }
-                float dv = 0.f;
-                if (t < p.L) {
-                    win[K - 1] = to_f(xr[j]);
-                    float v = bias;
-#pragma unroll
-                    for (int k = 0; k < K; ++k) v = fmaf(w[k], win[k], v);
-                    const float s = sigmoid_fast(v);
-                    dv = to_f(gr[j]) * s * fmaf(v, 1.0f - s, 1.0f);
-                    if (t < t1) {   // parameter gradients: own tile only
-                        db += dv;
-#pragma unroll
-                        for (int k = 0; k < K; ++k) dw[k] = fmaf(dv, win[k], dw[k]);
-                    }
-                }
-                dvw[K - 1] = dv;
                 const int s_out = t - (K - 1);   // dxin[s] = sum_k w[k] dv[s + K-1 - k]
-                if (s_out >= t0 && s_out < t1) {
+                ChanVec<T, V> o;
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+#pragma unroll
+                    for (int k = 0; k < K - 1; ++k) { win[i][k] = win[i][k + 1]; dvw[i][k] = dvw[i][k + 1]; }
+                    float dv = 0.f;
+                    if (t < p.L) {
+                        win[i][K - 1] = xr[j].get(i);
+                        float v = bias[i];
+#pragma unroll
+                        for (int k = 0; k < K; ++k) v = fmaf(w[i][k], win[i][k], v);
+                        const float sg = sigmoid_fast(v);
+                        dv = gr[j].get(i) * sg * fmaf(v, 1.0f - sg, 1.0f);
+                        if (t < t1) {   // parameter gradients: own tile only
+                            db[i] += dv;
+#pragma unroll
+                            for (int k = 0; k < K; ++k) dw[i][k] = fmaf(dv, win[i][k], dw[i][k]);
+                        }
+                    }
+                    dvw[i][K - 1] = dv;
                     float acc = 0.f;
 #pragma unroll
-                    for (int k = 0; k < K; ++k) acc = fmaf(w[k], dvw[K - 1 - k], acc);
-                    st_stream(dx + (int64_t)s_out * p.dx_rs, from_f<T>(acc));
+                    for (int k = 0; k < K; ++k) acc = fmaf(w[i][k], dvw[i][K - 1 - k], acc);
+                    o.set(i, acc);
                 }
+                if (s_out >= t0 && s_out < t1) o.store(dx + (int64_t)s_out * p.dx_rs);
             }
         }
     }
     float *part = p.part + ((size_t)(b * p.ntiles + tile) * (K + 1)) * p.ED + c;
 #pragma unroll
-    for (int k = 0; k < K; ++k) part[(size_t)k * p.ED] = dw[k];
-    part[(size_t)K * p.ED] = db;
+    for (int i = 0; i < V; ++i) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) part[(size_t)k * p.ED + i] = dw[i][k];
+        part[(size_t)K * p.ED + i] = db[i];
+    }
 }
 
+// block (32 channels, 8 slices of the B * ntiles partial rows): coalesced reads, 8-way split of the serial sum
 template <int K>
-__global__ void __launch_bounds__(128) conv1d_bwd_finalize_kernel(ConvParams p) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) conv1d_bwd_finalize_kernel(ConvParams p) {
+    __shared__ float s_acc[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
     const int k = blockIdx.y;   // 0..K
-    if (c >= p.ED) return;
     float acc = 0.f;
     const int n = p.B * p.ntiles;
-    for (int i = 0; i < n; ++i) acc += p.part[((size_t)i * (K + 1) + k) * p.ED + c];
-    if (k < K) p.dw[(size_t)c * K + k] = acc;
-    else if (p.dbias) p.dbias[c] = acc;
+    if (c < p.ED)
+        for (int i = threadIdx.y; i < n; i += 8) acc += p.part[((size_t)i * (K + 1) + k) * p.ED + c];
+    s_acc[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < p.ED) {
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t += s_acc[q][threadIdx.x];
+        if (k < K) p.dw[(size_t)c * K + k] = t;
+        else if (p.dbias) p.dbias[c] = t;
+    }
+}
+
+// channels per lane: 8-byte accesses when every base pointer and stride keeps them aligned, else one channel per lane
+template <typename T>
+static int conv_vec(const ConvParams &p, bool bwd) {
+    constexpr int V = 8 / (int)sizeof(T);
+    if (p.ED % V != 0) return 1;
+    auto ok = [&](const void *q, int64_t bs, int64_t rs) {
+        return q == nullptr || ((reinterpret_cast<uintptr_t>(q) & 7) == 0 && (bs * (int64_t)sizeof(T)) % 8 == 0 && (rs * (int64_t)sizeof(T)) % 8 == 0);
+    };
+    bool a = ok(p.xin, p.x_bs, p.x_rs);
+    a = a && (bwd ? ok(p.du, p.du_bs, p.du_rs) && ok(p.dxin, p.dx_bs, p.dx_rs) : ok(p.u, p.u_bs, p.u_rs));
+    return a ? V : 1;
 }
 
 template <typename T, int K>
 static int conv_fwd_launch(ConvParams &p, cudaStream_t st) {
-    const dim3 block(128), grid((p.ED + 127) / 128, p.ntiles, p.B);
+    constexpr int V = 8 / (int)sizeof(T);
+    const int v = conv_vec<T>(p, false);
+    const dim3 block(128), grid((p.ED / v + 127) / 128, p.ntiles, p.B);
     { ScopedKernelTimer tm(K_CONV_FWD, st);
-      conv1d_silu_fwd_kernel<T, K><<<grid, block, 0, st>>>(p); }
+      if (v == V) conv1d_silu_fwd_kernel<T, K, V><<<grid, block, 0, st>>>(p);
+      else conv1d_silu_fwd_kernel<T, K, 1><<<grid, block, 0, st>>>(p); }
     return check_launch("conv1d_silu_fwd");
 }
 
 template <typename T, int K>
 static int conv_bwd_launch(ConvParams &p, cudaStream_t st) {
-    const dim3 block(128), grid((p.ED + 127) / 128, p.ntiles, p.B);
+    constexpr int V = 8 / (int)sizeof(T);
+    const int v = conv_vec<T>(p, true);
+    const dim3 block(128), grid((p.ED / v + 127) / 128, p.ntiles, p.B);
     { ScopedKernelTimer tm(K_CONV_BWD, st);
-      conv1d_silu_bwd_kernel<T, K><<<grid, block, 0, st>>>(p); }
+      if (v == V) conv1d_silu_bwd_kernel<T, K, V><<<grid, block, 0, st>>>(p);
+      else conv1d_silu_bwd_kernel<T, K, 1><<<grid, block, 0, st>>>(p); }
     int rc = check_launch("conv1d_silu_bwd");
     if (rc != GFE_OK) return rc;
     { ScopedKernelTimer tm(K_CONV_BWD_FIN, st);
-      conv1d_bwd_finalize_kernel<K><<<dim3((p.ED + 127) / 128, K + 1), 128, 0, st>>>(p); }
+      conv1d_bwd_finalize_kernel<K><<<dim3((p.ED + 31) / 32, K + 1), dim3(32, 8), 0, st>>>(p); }
     return check_launch("conv1d_bwd_finalize");
 }
 
