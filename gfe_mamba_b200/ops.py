@@ -47,10 +47,36 @@ def _rows(t: torch.Tensor) -> torch.Tensor:
     return t if t.stride(-1) == 1 else t.contiguous()
 
 
+_SIZE_CACHE = {}
+
+
+def _sizes(B: int, L: int, ED: int, N: int):
+    """(ckpt, fwd workspace, bwd workspace) bytes of one shape; pure functions of the shape, so asked once."""
+    key = (B, L, ED, N)
+    v = _SIZE_CACHE.get(key)
+    if v is None:
+        l = nat.lib()
+        v = (l.gfe_selscan_ckpt_bytes(B, L, ED, N), l.gfe_selscan_fwd_workspace_bytes(B, L, ED, N),
+             l.gfe_selscan_bwd_workspace_bytes(B, L, ED, N))
+        _SIZE_CACHE[key] = v
+    return v
+
+
+def _as(t: torch.Tensor, dt: torch.dtype) -> torch.Tensor:
+    """detach + dtype + unit channel stride, touching the tensor only when something has to change."""
+    t = t.detach()
+    if t.dtype != dt:
+        t = t.to(dt)
+    return t if t.stride(-1) == 1 else t.contiguous()
+
+
 def _f32(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     if t is None:
         return None
-    return t.detach().float().contiguous()
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
 
 
 # ------------------------------------------------------------------------------------------ pscan
@@ -129,8 +155,8 @@ class _SelectiveScanFn(torch.autograd.Function):
                 or tuple(A_log.shape) != (ED, N) or tuple(D.shape) != (ED,):
             raise ValueError("selective_scan: inconsistent shapes")
         dt = u.dtype
-        u_, delta_, Bm_, Cm_ = (_rows(t.detach().to(dt)) for t in (u, delta, Bm, Cm))
-        z_ = None if z is None else _rows(z.detach().to(dt))
+        u_, delta_, Bm_, Cm_ = (_as(t, dt) for t in (u, delta, Bm, Cm))
+        z_ = None if z is None else _as(z, dt)
         A_log_, D_, bias_ = _f32(A_log), _f32(D), _f32(dt_bias)
         out = torch.empty((B, L, ED), dtype=dt, device=dev)
         last = torch.empty((B, ED, N), dtype=torch.float32, device=dev) if return_last_state else None
@@ -141,9 +167,10 @@ class _SelectiveScanFn(torch.autograd.Function):
         a.out, a.out_bs, a.out_rs = out.data_ptr(), out.stride(0), out.stride(1)
         a.last_state = 0 if last is None else last.data_ptr()
         with torch.cuda.device(dev):
-            nck = l.gfe_selscan_ckpt_bytes(B, L, ED, N) if need_grad else 0
+            sz = _sizes(B, L, ED, N)
+            nck = sz[0] if need_grad else 0
             ckpt = _bytes(nck, dev)
-            nws = l.gfe_selscan_fwd_workspace_bytes(B, L, ED, N)
+            nws = sz[1]
             ws = _bytes(nws, dev)
             a.ckpt, a.ckpt_bytes = (0 if ckpt is None else ckpt.data_ptr()), nck
             a.ws, a.ws_bytes = (0 if ws is None else ws.data_ptr()), nws
@@ -164,7 +191,7 @@ class _SelectiveScanFn(torch.autograd.Function):
         B, L, ED = u.shape
         N = A_log.shape[1]
         dt = u.dtype
-        dout = _rows(dout.detach().to(dt))
+        dout = _as(dout, dt)
         du = torch.empty((B, L, ED), dtype=dt, device=dev)
         ddelta = torch.empty((B, L, ED), dtype=dt, device=dev)
         dz = None if z is None else torch.empty((B, L, ED), dtype=dt, device=dev)
@@ -187,7 +214,7 @@ class _SelectiveScanFn(torch.autograd.Function):
         a.dA_log, a.dD = dA_log.data_ptr(), dD.data_ptr()
         a.ddt_bias = 0 if dbias is None else dbias.data_ptr()
         with torch.cuda.device(dev):
-            nws = l.gfe_selscan_bwd_workspace_bytes(B, L, ED, N)
+            nws = _sizes(B, L, ED, N)[2]
             ws = _bytes(nws, dev)
             a.ws, a.ws_bytes = (0 if ws is None else ws.data_ptr()), nws
             nat.check(l.gfe_selscan_bwd(ctypes.byref(a), _stream(dev)), "selscan_bwd")

@@ -52,7 +52,7 @@ def test_size_queries_without_gpu():
     assert lib.gfe_selscan_fwd_workspace_bytes(1, 65536, 1024, N) > 0   # cfg4 splits L
     assert lib.gfe_pscan_workspace_bytes(32, 256, 512, 16) == 0
     assert lib.gfe_pscan_workspace_bytes(1, 65536, 4, 16) > 0
-    assert lib.gfe_conv1d_bwd_workspace_bytes(2, 130, 64, 4) == 2 * 3 * 5 * 64 * 4
+    assert lib.gfe_conv1d_bwd_workspace_bytes(2, 130, 64, 4) == 2 * 2 * 5 * 64 * 4   # B x ceil(L / 128) tiles x (K + 1) x ED fp32
 
 
 def test_argument_validation_without_gpu():
