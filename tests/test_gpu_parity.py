@@ -533,6 +533,29 @@ def test_mamba_stack_fused_norm_matches_layerwise():
         assert relerr(gp[n], p.grad) < 1e-4, n
 
 
+def test_graphed_decoder_matches_step_loop():
+    """CUDA-graph decode (gfe_mamba_b200.decode.GraphedDecoder) == Mamba.step token by token == Mamba.forward."""
+    from gfe_mamba_b200 import Mamba, MambaConfig
+    from gfe_mamba_b200.decode import GraphedDecoder
+    torch.manual_seed(11)
+    cfg = MambaConfig(d_model=64, n_layers=3)
+    model = Mamba(cfg).cuda().eval()
+    B, T = 4, 12
+    x = torch.randn(B, T, cfg.d_model, device="cuda")
+    with torch.no_grad():
+        want = model(x)
+        caches = [(None, torch.zeros(B, cfg.d_inner, cfg.d_conv - 1, device="cuda")) for _ in range(cfg.n_layers)]
+        eager = []
+        for t in range(T):
+            yt, caches = model.step(x[:, t], caches)
+            eager.append(yt)
+        dec = GraphedDecoder(model, B)
+        graphed = [dec.step(x[:, t]).clone() for t in range(T)]
+    for t in range(T):
+        assert relerr(graphed[t], eager[t]) < 1e-6, t
+        assert relerr(graphed[t], want[:, t]) < 1e-4, t
+
+
 def test_error_behaviour():
     from gfe_mamba_b200 import selective_scan_fn, pscan
     with pytest.raises(RuntimeError, match="no CPU fallback"):
