@@ -67,7 +67,7 @@ class Mamba(nn.Module):
     def __init__(self, config: MambaConfig):
         super().__init__()
         self.config = config
-        self.layers = nn.ModuleList([ResidualBlock(config) for _ in range(config.n_layers)])
+        self.layers = nn.ModuleList(ResidualBlock(config) for _ in range(config.n_layers))
 
     def forward(self, x):
         # x : (B, L, D) -> (B, L, D)
@@ -85,8 +85,8 @@ class Mamba(nn.Module):
 
     def step(self, x, caches):
         # x : (B, D); caches : [(h, inputs)] per layer
-        for i, layer in enumerate(self.layers):
-            x, caches[i] = layer.step(x, caches[i])
+        for idx in range(len(self.layers)):
+            x, caches[idx] = self.layers[idx].step(x, caches[idx])
         return x, caches
 
 
@@ -102,8 +102,8 @@ class ResidualBlock(nn.Module):
         return self.mixer(self.norm(x)) + x
 
     def step(self, x, cache):
-        output, cache = self.mixer.step(self.norm(x), cache)
-        return output + x, cache
+        y, cache = self.mixer.step(self.norm(x), cache)
+        return y + x, cache
 
 
 class MambaBlock(nn.Module):
@@ -121,23 +121,21 @@ class MambaBlock(nn.Module):
         self.x_proj = nn.Linear(config.d_inner, config.dt_rank + 2 * config.d_state, bias=False)
         self.dt_proj = nn.Linear(config.dt_rank, config.d_inner, bias=True)
 
-        dt_init_std = config.dt_rank ** -0.5 * config.dt_scale
-        if config.dt_init == "constant":
-            nn.init.constant_(self.dt_proj.weight, dt_init_std)
-        elif config.dt_init == "random":
-            nn.init.uniform_(self.dt_proj.weight, -dt_init_std, dt_init_std)
-        else:
+        # dt_proj.weight: constant or uniform in +-dt_rank^-0.5 * dt_scale (mamba.py:141-148)
+        std = config.dt_rank ** -0.5 * config.dt_scale
+        initialisers = {"constant": lambda wt: nn.init.constant_(wt, std), "random": lambda wt: nn.init.uniform_(wt, -std, std)}
+        if config.dt_init not in initialisers:
             raise NotImplementedError
+        initialisers[config.dt_init](self.dt_proj.weight)
 
-        dt = torch.exp(
-            torch.rand(config.d_inner) * (math.log(config.dt_max) - math.log(config.dt_min)) + math.log(config.dt_min)
-        ).clamp(min=config.dt_init_floor)
-        inv_dt = dt + torch.log(-torch.expm1(-dt))  # inverse softplus
+        # dt_proj.bias = softplus^-1(dt), dt log-uniform in [dt_min, dt_max], floored (mamba.py:150-157)
+        log_lo, log_hi = math.log(config.dt_min), math.log(config.dt_max)
+        dt = torch.exp(torch.rand(config.d_inner) * (log_hi - log_lo) + log_lo).clamp(min=config.dt_init_floor)
         with torch.no_grad():
-            self.dt_proj.bias.copy_(inv_dt)
+            self.dt_proj.bias.copy_(dt + torch.log(-torch.expm1(-dt)))
 
-        A = torch.arange(1, config.d_state + 1, dtype=torch.float32).repeat(config.d_inner, 1)
-        self.A_log = nn.Parameter(torch.log(A))
+        # S4D-real initialisation A[c, n] = n + 1, stored as its logarithm (mamba.py:160-161)
+        self.A_log = nn.Parameter(torch.log(torch.arange(1, config.d_state + 1, dtype=torch.float32)).expand(config.d_inner, -1).clone())
         self.A_log._no_weight_decay = True
 
         self.D = nn.Parameter(torch.ones(config.d_inner))
@@ -145,25 +143,16 @@ class MambaBlock(nn.Module):
 
         self.out_proj = nn.Linear(config.d_inner, config.d_model, bias=config.bias)
 
-        if self.config.inner_layernorms:
-            self.dt_layernorm = RMSNorm(self.config.dt_rank, config.rms_norm_eps)
-            self.B_layernorm = RMSNorm(self.config.d_state, config.rms_norm_eps)
-            self.C_layernorm = RMSNorm(self.config.d_state, config.rms_norm_eps)
-        else:
-            self.dt_layernorm = None
-            self.B_layernorm = None
-            self.C_layernorm = None
+        # optional RMSNorm on dt, B, C (mamba.py:169-176); registration order dt, B, C as in the reference
+        widths = (config.dt_rank, config.d_state, config.d_state) if config.inner_layernorms else (0, 0, 0)
+        self.dt_layernorm, self.B_layernorm, self.C_layernorm = (
+            RMSNorm(n, config.rms_norm_eps) if n else None for n in widths)
         # config.use_cuda is accepted as-is: the fused sm_100a kernel *is* the CUDA path (no mamba_ssm import,
         # no fallback message, mamba.py:179-186).
 
     def _apply_layernorms(self, dt, B, C):
-        if self.dt_layernorm is not None:
-            dt = self.dt_layernorm(dt)
-        if self.B_layernorm is not None:
-            B = self.B_layernorm(B)
-        if self.C_layernorm is not None:
-            C = self.C_layernorm(C)
-        return dt, B, C
+        norms = (self.dt_layernorm, self.B_layernorm, self.C_layernorm)
+        return tuple(t if norm is None else norm(t) for norm, t in zip(norms, (dt, B, C)))
 
     # ------------------------------------------------------------------ training / prefill
     def forward(self, x):
