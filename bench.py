@@ -171,6 +171,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-rows", type=int, default=0, help="batch rows per pipeline chunk of the e2e leg (0 = B/4)")
     ap.add_argument("--batch", type=int, default=0, help="override the workload's per-GPU batch (A/B measurements)")
+    ap.add_argument("--shard", default="batch", choices=["batch", "channels"],
+                    help="N > 1: batch = every rank its own B rows (weak scaling); channels = ONE batch, rank g owns ED/N channels, "
+                         "dB/dC all-reduced every step (strong scaling; BASELINE config 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not bind the process to the GPU's NUMA node for the e2e leg")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
@@ -182,11 +185,16 @@ def main():
     B, L, d_model, dts = WORKLOADS[args.workload]
     B = args.batch or B
     dts = args.dtype or dts
-    ED = 2 * d_model
+    ED_full = 2 * d_model
+    by_channels = args.shard == "channels" and world > 1
+    if by_channels and ED_full % (32 * world) != 0:
+        raise SystemExit(f"bench.py: ED={ED_full} does not split into {world} channel shards of a multiple of 32")
+    ED = ED_full // world if by_channels else ED_full      # channels THIS rank scans
     s_bytes = 4 if dts == "f32" else 2
     cfg = {"workload": f"{args.workload}: fused selective scan fwd+bwd, B={B}/GPU, L={L}, d_model={d_model}, ED={ED}, N={N_STATE}",
            "batch_per_gpu": B, "seq_len": L, "d_inner": ED, "d_state": N_STATE,
-           "sharding": f"batch x{world}" if world > 1 else "single GPU",
+           "sharding": (f"channels x{world} (ED/{world} = {ED} per GPU, one batch, dB/dC all-reduced)" if by_channels
+                        else f"batch x{world}" if world > 1 else "single GPU"),
            "l2_policy": "inputs larger than L2" if 4 * B * L * ED * s_bytes > 2 * 126e6 else "rotating input sets + L2 flush"}
     warmup = max(args.warmup, 3)
 
@@ -221,14 +229,16 @@ def main():
 
     # ---- synthetic inputs, resident in HBM; small workloads rotate over several sets + flush L2
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    gen_shared = torch.Generator(device=dev).manual_seed(4321)   # B and C are replicated under channel sharding
     per_set = (4 * B * L * ED + 2 * B * L * N_STATE) * s_bytes
     nsets = 1 if per_set > 2 * 126e6 else min(8, int(4 * 126e6 // per_set) + 2)
 
     def make_set():
         rn = lambda *s: torch.randn(*s, device=dev, generator=gen)
+        rs = (lambda *s: torch.randn(*s, device=dev, generator=gen_shared)) if by_channels else rn
         return dict(u=rn(B, L, ED).to(dt).requires_grad_(), delta=(rn(B, L, ED) * 0.5).to(dt).requires_grad_(),
-                    z=rn(B, L, ED).to(dt).requires_grad_(), Bm=rn(B, L, N_STATE).to(dt).requires_grad_(),
-                    Cm=rn(B, L, N_STATE).to(dt).requires_grad_(), dout=rn(B, L, ED).to(dt))
+                    z=rn(B, L, ED).to(dt).requires_grad_(), Bm=rs(B, L, N_STATE).to(dt).requires_grad_(),
+                    Cm=rs(B, L, N_STATE).to(dt).requires_grad_(), dout=rn(B, L, ED).to(dt))
 
     sets = [make_set() for _ in range(nsets)]
     A_log = (torch.log(torch.arange(1, N_STATE + 1, device=dev).float()).repeat(ED, 1) + 0.1 * torch.randn(ED, N_STATE, device=dev, generator=gen)).requires_grad_()
@@ -241,7 +251,10 @@ def main():
         d = sets[i % nsets]
         out = selective_scan_fn(d["u"], d["delta"], A_log, d["Bm"], d["Cm"], D, z=d["z"], dt_bias=bias)
         grads = torch.autograd.grad(out, (d["u"], d["delta"], d["z"], d["Bm"], d["Cm"], A_log, D, bias), d["dout"])
-        if world > 1:   # data-parallel training: all-reduce the (tiny) parameter gradients
+        if by_channels:   # channel sharding: dB, dC sum over every rank's channels (2 B L N values); parameters are local
+            flat = torch.cat([grads[3].reshape(-1), grads[4].reshape(-1)]).float()
+            dist.all_reduce(flat)
+        elif world > 1:   # data-parallel training: all-reduce the (tiny) parameter gradients
             flat = torch.cat([g.reshape(-1) for g in grads[5:]])
             dist.all_reduce(flat)
         return out, grads
@@ -290,7 +303,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
     ms_per_step = elapsed_ms / args.steps
-    tokens_per_s = world * B * L / (ms_per_step * 1e-3)
+    tokens_per_s = (1 if by_channels else world) * B * L / (ms_per_step * 1e-3)   # channel sharding: ONE batch of tokens
 
     # ---- roofline of the dominant kernel + every kernel's share
     peak, peak_src = measured_peaks()
@@ -344,7 +357,7 @@ def main():
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e = {"value": world * B * L / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
+    e2e = {"value": (1 if by_channels else world) * B * L / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
            "ms_per_step": round(e2e_s * 1e3, 3), "steps": args.e2e_steps, "rows_per_chunk": pipe.rows, "host_cpus": numa_cpus,
            "api": "gfe_mamba_b200.host_pipeline.HostScanPipeline.run (pinned host in/out, H2D | fwd+bwd | D2H overlapped over row chunks)"}
 
@@ -359,7 +372,7 @@ def main():
     if rank == 0:
         line = {"metric": "selective-scan fwd+bwd tokens/s", "value": tokens_per_s, "unit": "tokens/s", "n_gpus": world,
                 "steps": args.steps, "warmup": warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": dts, "data": "synthetic", "config": cfg,
+                "scaling": "strong" if by_channels else "weak", "vs_baseline": None, "dtype": dts, "data": "synthetic", "config": cfg,
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
                 "kernels": kern_list}
         print(json.dumps(line), file=out_stream, flush=True)
