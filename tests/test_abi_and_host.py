@@ -185,3 +185,27 @@ def test_host_pipeline_requires_cuda():
         pytest.skip("CUDA present")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         HostScanPipeline(2, 8, 32, 16, torch.float32, torch.device("cpu"))
+
+
+def test_bench_helpers():
+    """bench.py's byte accounting and the traffic lookup keyed by workload and per-GPU batch."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    fwd, bwd = bench.algorithmic_bytes(16, 4096, 1536, 2)
+    assert fwd == 16 * 4096 * (4 * 1536 + 2 * 16) * 2 == 809500672
+    assert bwd == 16 * 4096 * (7 * 1536 + 4 * 16) * 2 == 1417674752
+    t = bench.measured_traffic("cfg3", "selscan_bwd", 16)
+    assert t is None or t > bwd                      # checkpoints, saved y and the dB|dC rows ride on top of the algorithmic bytes
+    assert bench.measured_traffic("cfg3", "selscan_bwd", 3) is None and bench.measured_traffic("nope", "selscan_bwd", 16) is None
+
+
+def test_numa_binding_is_a_no_op_without_topology():
+    import torch
+    from gfe_mamba_b200.host_pipeline import bind_host_to_gpu_node
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    before = os.sched_getaffinity(0)
+    assert bind_host_to_gpu_node(torch.device("cpu")) is None
+    assert os.sched_getaffinity(0) == before
