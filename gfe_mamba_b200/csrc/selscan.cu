@@ -26,7 +26,6 @@
 
 #include "common.cuh"
 #include "selscan_shared.cuh"
-#include "selscan_v3.cuh"
 
 namespace gfe {
 
@@ -635,10 +634,12 @@ static int fast_path_cpb(const gfe_selscan_args *a, bool bwd) {
         ok16 &= (st * s) % 16 == 0;
         ok4 &= (st * s) % 4 == 0;
     }
-    if (const char *e = getenv("GFE_SELSCAN_PATH")) {   // debugging / A-B measurements only
+#ifdef GFE_EXPERIMENTS
+    if (const char *e = getenv("GFE_SELSCAN_PATH")) {   // A/B measurements only (experiments build)
         if (!strcmp(e, "generic")) return 0;
         if (!strcmp(e, "cp4")) ok16 = false;
     }
+#endif
     return ok16 ? 16 : (ok4 ? 4 : 0);
 }
 
@@ -869,22 +870,20 @@ extern "C" {
 GFE_API size_t gfe_selscan_ckpt_bytes(int B, int L, int ED, int N) {
     if (B <= 0 || L <= 0 || ED <= 0 || N != gfe::kNState) return 0;
     // chunk-start states (fp32) + y before the gate (up to 4 bytes per element)
-    if (gfe::v3_shape_ok(B, L, ED) || gfe::v2_applicable(B, L, ED))
+    if (gfe::chain_applicable(B, L, ED))
         return (size_t)B * ((L + gfe::kCkptV2 - 1) / gfe::kCkptV2) * ED * gfe::kNState * sizeof(float) + (size_t)B * L * ED * sizeof(float);
     return gfe::ckpt_state_bytes(B, L, ED) + (size_t)B * L * ED * sizeof(float);
 }
 
 GFE_API size_t gfe_selscan_fwd_workspace_bytes(int B, int L, int ED, int N) {
     if (B <= 0 || L <= 0 || ED <= 0 || N != gfe::kNState) return 0;
-    if (gfe::v3_shape_ok(B, L, ED)) return gfe::v3_fwd_workspace_bytes(B, L, ED);
-    if (gfe::v2_applicable(B, L, ED)) return gfe::v2_fwd_workspace_bytes(B, L, ED);
+    if (gfe::chain_applicable(B, L, ED)) return gfe::chain_fwd_workspace_bytes(B, L, ED);
     return gfe::fwd_ws_layout(B, L, ED, gfe::plan_segments(B, L, ED)).total;
 }
 
 GFE_API size_t gfe_selscan_bwd_workspace_bytes(int B, int L, int ED, int N) {
     if (B <= 0 || L <= 0 || ED <= 0 || N != gfe::kNState) return 0;
-    if (gfe::v3_shape_ok(B, L, ED)) return gfe::v3_bwd_workspace_bytes(B, L, ED);
-    if (gfe::v2_applicable(B, L, ED)) return gfe::v2_bwd_workspace_bytes(B, L, ED);
+    if (gfe::chain_applicable(B, L, ED)) return gfe::chain_bwd_workspace_bytes(B, L, ED);
     return gfe::bwd_ws_layout(B, L, ED, gfe::plan_segments(B, L, ED)).total;
 }
 
@@ -892,8 +891,7 @@ GFE_API int gfe_selscan_fwd(const gfe_selscan_args *a, void *stream) {
     int rc = gfe::validate_common(a, false);
     if (rc != GFE_OK) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (gfe::v3_shape_ok(a->batch, a->seqlen, a->d_inner)) return gfe::v3_launch_fwd(a, st);
-    if (gfe::v2_applicable(a->batch, a->seqlen, a->d_inner)) return gfe::v2_launch_fwd(a, st);
+    if (gfe::chain_applicable(a->batch, a->seqlen, a->d_inner)) return gfe::chain_launch_fwd(a, st);
     switch (a->dtype) {
         case GFE_F32: return gfe::launch_fwd<float>(a, st);
         case GFE_BF16: return gfe::launch_fwd<__nv_bfloat16>(a, st);
@@ -905,8 +903,7 @@ GFE_API int gfe_selscan_bwd(const gfe_selscan_args *a, void *stream) {
     int rc = gfe::validate_common(a, true);
     if (rc != GFE_OK) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (gfe::v3_shape_ok(a->batch, a->seqlen, a->d_inner)) return gfe::v3_launch_bwd(a, st);
-    if (gfe::v2_applicable(a->batch, a->seqlen, a->d_inner)) return gfe::v2_launch_bwd(a, st);
+    if (gfe::chain_applicable(a->batch, a->seqlen, a->d_inner)) return gfe::chain_launch_bwd(a, st);
     switch (a->dtype) {
         case GFE_F32: return gfe::launch_bwd<float>(a, st);
         case GFE_BF16: return gfe::launch_bwd<__nv_bfloat16>(a, st);

@@ -1,0 +1,597 @@
+// selscan_chain_bwd.cu -- fused selective-scan backward, chained L-segments, two channels x four states per lane.
+// Replaces autograd through mamba.py:255-256, 275-284, 220-222 and PScan.backward (pscan.py:189-224).
+//
+// Same lane layout as the forward kernel (selscan_v4_fwd.cu): a CTA of 2 * CPC threads serves CPC adjacent channels of
+// one batch row; lane (pair, quad) owns the states 4q..4q+3 of channels 2p and 2p + 1 as four float2 pairs.  Against the
+// first chained backward (one channel per lane, experiments/selscan_v2_bwd.cu) every B|C quad fetched from shared memory
+// feeds eight state-steps instead of four, the first level of the cross-channel dB|dC sums is an FFMA in the lane, the
+// shuffle reduction runs over half as many values, and the per-(t, channel) sums over states leave the lane as ONE
+// 16-byte store.  Per lane and step (8 state-steps): 6 LDS + 48 packed FP32 + 16 exp2 + 7 SHFL + 1 STS.128.
+//
+// Per unit = (L-segment, batch row, channel block), segments walked last to first (ChainSched, see selscan_shared.cuh):
+//   chunks of 16 steps are staged by cp.async (u, delta, dout, [y, z], B, C) and walked in reverse:
+//   phase A  (item mapping, thread per (t, channel pair)): softplus and its derivative, dy = dout * silu(z), dz, the
+//            slots {dl0, dl0 u0, dl1, dl1 u1}, {dy0, dy1}, {u0, sg0, u1, sg1}; B|C rows -> fp32 quads (natural and
+//            pair-swapped plane);
+//   phase B  (recurrence mapping), per half chunk of 8 steps: a forward sweep re-derives the 8 states from the half's
+//            checkpoint into registers; the reverse sweep runs g[t] = C dy + a[t+1] g[t+1] and forms every contraction
+//            with packed FP32 ops; dB|dC are reduced over the 8 pairs of the warp in groups of 2 steps (14 SHFL per 16
+//            values; the first level needs no selects because odd pairs hold their state pairs swapped);
+//   phase C  (warp-local item mapping, right after each half: only __syncwarp): du, ddelta from the four quads'
+//            partials; dD / ddt_bias accumulation;
+//   then the warps' dB|dC rows are added and leave as one row per (CTA, t) for selscan_bwd_finalize_bc.
+#include "common.cuh"
+#include "selscan_shared.cuh"
+
+namespace gfe {
+
+void chain_bwd_plan(int B, int L, int ED, int &cpc, int &nblk, int &nseg, int &seg_len);
+int chain_fill_sched(ChainSched &cs, char *ws, int B, int ED, int nblk, int nseg, int seg_len, cudaStream_t st);
+size_t chain_bytes(int B, int ED, int nblk, int nseg);
+void chain_fill_params(ScanParams &p, const gfe_selscan_args *a);
+int chain_cpb(const gfe_selscan_args *a, bool bwd);
+bool chain_pair_stores(const gfe_selscan_args *a, bool bwd);
+int chain_check_alignment(const gfe_selscan_args *a);
+void launch_bwd_finalize(const gfe_selscan_args *a, ScanParams &p, cudaStream_t st, int &rc);   // selscan.cu
+
+#ifndef GFE_CBWD_MINB
+#define GFE_CBWD_MINB 3        // CTAs of 128 threads per SM the register budget is set for (168 registers)
+#endif
+constexpr int kCRedRow = 36;   // padded row (floats) of the per-warp dB|dC tile: [t][n]{dB, dC}
+constexpr int kCBCPlane = kChunk * 8 + 4;   // float4 per B|C plane; the 64 B skew keeps the natural and the pair-swapped plane
+                                            // (read by the even / odd pairs of one quarter-warp) on disjoint banks
+
+template <typename T, bool HAS_Z, int CPC>
+struct BwdChainSmem {
+    static constexpr int kStages = 2;
+    static constexpr int NP = CPC / 2;
+    static constexpr int NW = CPC / 16;                                 // warps per CTA
+    static constexpr int kTile = kChunk * CPC * (int)sizeof(T);         // one of u, delta, dout, y, z
+    static constexpr int kNTile = HAS_Z ? 5 : 3;
+    static constexpr int kBCRaw = kChunk * kNState * (int)sizeof(T);     // one of B, C
+    static constexpr int kStage = kNTile * kTile + 2 * kBCRaw;
+    static constexpr int kSPlane = NP + 2;                               // float4 per (t, quad) plane of the partials (+32 B skew)
+    static constexpr int kOffDD = kStages * kStage;                      // float4 [16][NP] {dl0, dl0 u0, dl1, dl1 u1}
+    static constexpr int kOffDY = kOffDD + kChunk * NP * 16;             // float2 [16][NP] {dy0, dy1}
+    static constexpr int kOffEpi = kOffDY + kChunk * NP * 8;             // float4 [16][NP] {u0, softplus'0, u1, softplus'1}
+    static constexpr int kOffBC = kOffEpi + kChunk * NP * 16;            // float4 [2][16][8] (+64 B skew) B quads | C quads
+    static constexpr int kOffS = kOffBC + 2 * kCBCPlane * 16;            // float4 [8][4][NP + 2] {S1_0, S2_0, S1_1, S2_1} of one half chunk
+    static constexpr int kOffRed = kOffS + kCkptV2 * 4 * kSPlane * 16;   // float  [NW][16][36] per-warp dB|dC rows
+    static constexpr int kTotal = kOffRed + NW * kChunk * kCRedRow * 4;
+};
+
+template <typename T, bool HAS_Z, int CPB, int CPC>
+__global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_bwd_chain_kernel(ScanParams p, ChainSched cs) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int s_unit;
+    using SM = BwdChainSmem<T, HAS_Z, CPC>;
+    constexpr int NT = 2 * CPC, NP = SM::NP, NW = SM::NW, NST = SM::kStages, NTILE = SM::kNTile;
+    constexpr int RB = CPC * (int)sizeof(T);          // bytes per activation tile row
+    constexpr int PPT = kChunk * RB / 16 / NT;        // 16-byte pieces per thread per activation tile (1 for 16-bit, 2 for fp32)
+    constexpr int BCP = kChunk * kNState * (int)sizeof(T) / 16;   // pieces per B (or C) tile: 32 (16-bit), 64 (fp32)
+    constexpr int BCI = (2 * BCP + NT - 1) / NT;      // B|C pieces per thread
+    constexpr int BCC = kChunk * 8 / NT;              // fp32 B|C quads converted per thread
+    constexpr int SPL = SM::kSPlane;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rp = tid >> 2, rq = tid & 3;     // recurrence mapping: channel pair in block, state quad
+    const int sw = rp & 1;                     // odd pairs hold their state pairs swapped (select-free first reduce level)
+    const int ip = tid % NP, ir = tid / NP;    // phase A mapping: channel pair, rows ir + 4 i
+    const int cp = warp * 8 + (lane & 7), cr = lane >> 3;   // phase C mapping (warp-local): channel pair, rows cr + 4 i of a half
+
+    float4 *sDD = reinterpret_cast<float4 *>(smem + SM::kOffDD);
+    float2 *sDY = reinterpret_cast<float2 *>(smem + SM::kOffDY);
+    float4 *sEpi = reinterpret_cast<float4 *>(smem + SM::kOffEpi);
+    float4 *sBC = reinterpret_cast<float4 *>(smem + SM::kOffBC);
+    float4 *sS = reinterpret_cast<float4 *>(smem + SM::kOffS);
+    float *sRed = reinterpret_cast<float *>(smem + SM::kOffRed);
+    const bool sp = p.flags & GFE_FLAG_DELTA_SOFTPLUS;
+    const bool vec = p.flags & kFlagPairStores;
+    const int per_seg = p.B * cs.nblk;
+
+    // recurrence-side shared pointers (fixed for the whole kernel)
+    const float4 *dd_r = sDD + rp;
+    const float2 *dy_r = sDY + rp;
+    const float4 *bc_r = sBC + sw * kCBCPlane + rq;
+    float4 *s_w = sS + rq * SPL + rp;
+    const bool up8 = (lane & 8) != 0, up16 = (lane & 16) != 0;
+    float *red_w = sRed + warp * (kChunk * kCRedRow) + (up16 ? kCRedRow : 0) + 2 * (4 * rq + (up8 ? 2 : 0) + sw);
+
+    // staging geometry of this thread (fixed)
+    const int srow = (tid * PPT) / (RB / 16), spiece = (tid * PPT) % (RB / 16);   // PPT consecutive pieces of one row
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_unit = atomicAdd(cs.counter, 1);
+        __syncthreads();
+        const int unit = s_unit;
+        if (unit >= cs.total) break;
+        const int rseg = unit / per_seg;           // processing order: last time segment first
+        const int seg = cs.nseg - 1 - rseg;
+        const int rem = unit - rseg * per_seg;
+        const int b = rem / cs.nblk;
+        const int blk = rem - b * cs.nblk;
+        const int c0 = blk * CPC;
+        const int t0 = seg * cs.seg_len, t1 = min(p.L, t0 + cs.seg_len);
+        const int kfirst = t0 / kChunk, klast = (t1 - 1) / kChunk;   // global chunk indices, walked klast .. kfirst
+        const int nch = klast - kfirst + 1;
+
+        const T *ub = reinterpret_cast<const T *>(p.u) + (int64_t)b * p.u_bs + c0;
+        const T *db = reinterpret_cast<const T *>(p.delta) + (int64_t)b * p.d_bs + c0;
+        const T *gb = reinterpret_cast<const T *>(p.dout) + (int64_t)b * p.do_bs + c0;
+        const T *yb = reinterpret_cast<const T *>(p.ysave) + (int64_t)b * p.L * p.ED + c0;
+        const T *zb = HAS_Z ? reinterpret_cast<const T *>(p.z) + (int64_t)b * p.z_bs + c0 : nullptr;
+        const T *Bb = reinterpret_cast<const T *>(p.Bm) + (int64_t)b * p.B_bs;
+        const T *Cb = reinterpret_cast<const T *>(p.Cm) + (int64_t)b * p.C_bs;
+        // this lane's checkpointed quads: [b][t / 8][c][16] fp32, channels 2 rp and 2 rp + 1
+        const float4 *ckq = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(p.ckpt) +
+                                                             ((size_t)b * p.nchunks * p.ED + c0 + 2 * rp) * kNState) + rq;
+        const size_t ck_step = (size_t)p.ED * (kNState / 4);   // float4 between consecutive checkpoints
+        T *dub = reinterpret_cast<T *>(p.du) + (int64_t)b * p.du_bs + c0 + 2 * cp;
+        T *ddb = reinterpret_cast<T *>(p.ddelta) + (int64_t)b * p.dd_bs + c0 + 2 * cp;
+        T *dzb = HAS_Z ? reinterpret_cast<T *>(p.dz) + (int64_t)b * p.dz_bs + c0 + 2 * ip : nullptr;
+
+        // per-thread source pointers of the staged pieces at row 0 of this batch row (cp.async path)
+        const char *su = nullptr, *sd = nullptr, *sg_ = nullptr, *sy = nullptr, *sz = nullptr, *sbc[BCI];
+        int64_t rs_bc[BCI];
+        int bcrow[BCI];
+        if constexpr (CPB == 16) {
+            su = reinterpret_cast<const char *>(ub + (int64_t)srow * p.u_rs) + spiece * 16;
+            sd = reinterpret_cast<const char *>(db + (int64_t)srow * p.d_rs) + spiece * 16;
+            sg_ = reinterpret_cast<const char *>(gb + (int64_t)srow * p.do_rs) + spiece * 16;
+            if (HAS_Z) {
+                sy = reinterpret_cast<const char *>(yb + (int64_t)srow * p.ED) + spiece * 16;
+                sz = reinterpret_cast<const char *>(zb + (int64_t)srow * p.z_rs) + spiece * 16;
+            }
+#pragma unroll
+            for (int i = 0; i < BCI; ++i) {
+                const int pc = tid + i * NT;
+                const int sel = pc / BCP, within = pc % BCP;    // 0: B, 1: C
+                bcrow[i] = within / (BCP / kChunk);
+                rs_bc[i] = (sel ? p.C_rs : p.B_rs) * (int64_t)sizeof(T);
+                sbc[i] = reinterpret_cast<const char *>((sel ? Cb : Bb)) + bcrow[i] * rs_bc[i] + (within % (BCP / kChunk)) * 16;
+            }
+        }
+        const uint32_t dst_act = smem_u32(smem) + srow * RB + spiece * 16;
+        const uint32_t dst_bc = smem_u32(smem) + NTILE * SM::kTile + tid * 16;   // raw B tile followed by raw C tile
+
+        auto issue = [&](int i) {   // i-th chunk in processing order (global chunk klast - i) -> stage i % NST
+            if (i < nch) {
+                const int tb = (klast - i) * kChunk;
+                const int nrows = min(kChunk, t1 - tb);
+                const uint32_t so = (i % NST) * SM::kStage;
+                if constexpr (CPB == 16) {
+                    if (srow < nrows) {
+                        const int64_t sz_t = (int64_t)sizeof(T);
+#pragma unroll
+                        for (int q = 0; q < PPT; ++q) {
+                            cp_async<16>(dst_act + so + q * 16, su + (int64_t)tb * p.u_rs * sz_t + q * 16);
+                            cp_async<16>(dst_act + so + SM::kTile + q * 16, sd + (int64_t)tb * p.d_rs * sz_t + q * 16);
+                            cp_async<16>(dst_act + so + 2 * SM::kTile + q * 16, sg_ + (int64_t)tb * p.do_rs * sz_t + q * 16);
+                            if (HAS_Z) {
+                                cp_async<16>(dst_act + so + 3 * SM::kTile + q * 16, sy + (int64_t)tb * p.ED * sz_t + q * 16);
+                                cp_async<16>(dst_act + so + 4 * SM::kTile + q * 16, sz + (int64_t)tb * p.z_rs * sz_t + q * 16);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < BCI; ++q)
+                        if (tid + q * NT < 2 * BCP && bcrow[q] < nrows) cp_async<16>(dst_bc + so + q * NT * 16, sbc[q] + (int64_t)tb * rs_bc[q]);
+                } else {
+                    unsigned char *s = smem + so;
+                    stage_tile<T, 0, CPC, NT>(s, ub + (int64_t)tb * p.u_rs, p.u_rs, nrows, tid);
+                    stage_tile<T, 0, CPC, NT>(s + SM::kTile, db + (int64_t)tb * p.d_rs, p.d_rs, nrows, tid);
+                    stage_tile<T, 0, CPC, NT>(s + 2 * SM::kTile, gb + (int64_t)tb * p.do_rs, p.do_rs, nrows, tid);
+                    if (HAS_Z) {
+                        stage_tile<T, 0, CPC, NT>(s + 3 * SM::kTile, yb + (int64_t)tb * p.ED, p.ED, nrows, tid);
+                        stage_tile<T, 0, CPC, NT>(s + 4 * SM::kTile, zb + (int64_t)tb * p.z_rs, p.z_rs, nrows, tid);
+                    }
+                    unsigned char *sb = s + NTILE * SM::kTile;
+                    stage_tile<T, 0, kNState, NT>(sb, Bb + (int64_t)tb * p.B_rs, p.B_rs, nrows, tid);
+                    stage_tile<T, 0, kNState, NT>(sb + SM::kBCRaw, Cb + (int64_t)tb * p.C_rs, p.C_rs, nrows, tid);
+                }
+            }
+            cp_async_commit();
+        };
+#pragma unroll
+        for (int i = 0; i < NST; ++i) issue(i);
+
+        // per-thread constants (state pairs swapped when sw)
+        float2 A2[2][2], G[2][2], dA[2][2];
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(p.A_log + (size_t)(c0 + 2 * rp + ch) * kNState) + rq);
+            const float a0 = -expf(v.x) * kLog2e, a1 = -expf(v.y) * kLog2e, a2 = -expf(v.z) * kLog2e, a3 = -expf(v.w) * kLog2e;
+            A2[ch][0] = sw ? make_float2(a1, a0) : make_float2(a0, a1);
+            A2[ch][1] = sw ? make_float2(a3, a2) : make_float2(a2, a3);
+            dA[ch][0] = dA[ch][1] = make_float2(0.f, 0.f);
+        }
+        const float2 bias = p.dt_bias ? __ldg(reinterpret_cast<const float2 *>(p.dt_bias + c0) + ip) : make_float2(0.f, 0.f);   // phase A pair
+        const float2 Dc = __ldg(reinterpret_cast<const float2 *>(p.D + c0) + cp);                                                // phase C pair
+        float2 dD_acc = make_float2(0.f, 0.f), dbias_acc = make_float2(0.f, 0.f);
+
+        float *carry = cs.carry + ((size_t)b * p.ED + c0 + 2 * rp) * kNState + 4 * rq;
+        if (rseg > 0) {
+            if (tid == 0) {
+                const int *f = cs.flags + (unit - per_seg);
+                while (ld_acquire(f) == 0) __nanosleep(100);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                const float4 v = __ldcg(reinterpret_cast<const float4 *>(carry + ch * kNState));
+                G[ch][0] = sw ? make_float2(v.y, v.x) : make_float2(v.x, v.y);
+                G[ch][1] = sw ? make_float2(v.w, v.z) : make_float2(v.z, v.w);
+            }
+        } else {
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) G[ch][0] = G[ch][1] = make_float2(0.f, 0.f);
+        }
+
+        auto phase_a = [&](int i) {
+            const int tb = (klast - i) * kChunk;
+            const unsigned char *s = smem + (i % NST) * SM::kStage;
+            const T *sU = reinterpret_cast<const T *>(s);
+            const T *sD = reinterpret_cast<const T *>(s + SM::kTile);
+            const T *sDo = reinterpret_cast<const T *>(s + 2 * SM::kTile);
+            const T *sY = reinterpret_cast<const T *>(s + 3 * SM::kTile);
+            const T *sZ = reinterpret_cast<const T *>(s + 4 * SM::kTile);
+            const T *sBr = reinterpret_cast<const T *>(s + NTILE * SM::kTile);
+            float2 dl[4], sg[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {   // branch-free packed softplus + sigmoid (selscan_shared.cuh)
+                const float2 d2 = lds_pair(sD + (ir + 4 * q) * CPC, ip);
+                const float2 x = make_float2(d2.x + bias.x, d2.y + bias.y);
+                float2 sg2;
+                const float2 v = softplus2<true>(x, sg2);
+                dl[q] = sp ? v : x;
+                sg[q] = sp ? sg2 : make_float2(1.0f, 1.0f);
+            }
+            float2 uq[4], gq[4], zq[4], yq[4];   // every load of the phase before its first store (an LDS is never moved above an STS)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int t = ir + 4 * q;
+                uq[q] = lds_pair(sU + t * CPC, ip);
+                gq[q] = lds_pair(sDo + t * CPC, ip);
+                if (HAS_Z) {
+                    zq[q] = lds_pair(sZ + t * CPC, ip);
+                    yq[q] = lds_pair(sY + t * CPC, ip);
+                }
+            }
+            float4 bcv[BCC];
+#pragma unroll
+            for (int q = 0; q < BCC; ++q) {
+                const int e = tid + q * NT, t = e >> 3, q8 = e & 7;
+                bcv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (tb + t < t1) {
+                    const T *src = sBr + (q8 < 4 ? 0 : kChunk * 16) + t * 16 + 4 * (q8 & 3);
+                    const float2 lo = lds_pair(src, 0), hi = lds_pair(src, 1);
+                    bcv[q] = make_float4(lo.x, lo.y, hi.x, hi.y);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int t = ir + 4 * q;
+                const bool valid = tb + t < t1;
+                const float u0 = valid ? uq[q].x : 0.f, u1 = valid ? uq[q].y : 0.f;
+                const float do0 = valid ? gq[q].x : 0.f, do1 = valid ? gq[q].y : 0.f;
+                const float dl0 = valid ? dl[q].x : 0.f, dl1 = valid ? dl[q].y : 0.f;   // padded step: a = 1, bx = 0, dy = 0
+                float dy0 = do0, dy1 = do1;
+                if (HAS_Z) {
+                    const float z0 = valid ? zq[q].x : 0.f, z1 = valid ? zq[q].y : 0.f;
+                    const float sz0 = sigmoid_fast(z0), sz1 = sigmoid_fast(z1);
+                    dy0 = do0 * (z0 * sz0);
+                    dy1 = do1 * (z1 * sz1);
+                    if (valid) {   // dz = dout * d silu(z)/dz * y needs nothing from the sweeps
+                        const float f0 = do0 * sz0 * fmaf(z0, 1.0f - sz0, 1.0f), f1 = do1 * sz1 * fmaf(z1, 1.0f - sz1, 1.0f);
+                        stg_pair<T>(dzb + (int64_t)(tb + t) * p.dz_rs, f0 * yq[q].x, f1 * yq[q].y, vec);
+                    }
+                }
+                sDD[t * NP + ip] = make_float4(dl0, dl0 * u0, dl1, dl1 * u1);
+                sDY[t * NP + ip] = make_float2(dy0, dy1);
+                sEpi[t * NP + ip] = make_float4(u0, sg[q].x, u1, sg[q].y);
+            }
+            // B|C rows as fp32 quads, natural and pair-swapped order: [sw][t][B quads 0..3 | C quads 0..3]
+#pragma unroll
+            for (int q = 0; q < BCC; ++q) {
+                sBC[tid + q * NT] = bcv[q];
+                sBC[kCBCPlane + tid + q * NT] = make_float4(bcv[q].y, bcv[q].x, bcv[q].w, bcv[q].z);
+            }
+        };
+
+        cp_async_wait<NST - 1>();
+        __syncthreads();
+        phase_a(0);
+        // checkpoints of the first chunk (states before its steps 0 and 8), both channels
+        float4 ck_lo[2], ck_hi[2];
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            ck_lo[ch] = __ldcs(ckq + (size_t)(2 * klast) * ck_step + ch * (kNState / 4));
+            ck_hi[ch] = (klast * kChunk + kCkptV2 < t1) ? __ldcs(ckq + (size_t)(2 * klast + 1) * ck_step + ch * (kNState / 4))
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+
+        for (int i = 0; i < nch; ++i) {
+            const int k = klast - i;
+            const int tb = k * kChunk;
+            __syncthreads();   // (1) slots of this chunk are complete
+
+#pragma unroll 1
+            for (int half = 1; half >= 0; --half) {   // steps 8..15, then 0..7 (one copy of the sweep code)
+                const int jo = half * kCkptV2;
+                if (tb + jo >= t1) continue;          // block-uniform: the half lies beyond the sequence
+                // ------------------------------------------------------------ phase B
+                const float4 *dd_p = dd_r + jo * NP;
+                const float2 *dy_p = dy_r + jo * NP;
+                const float4 *bc_p = bc_r + jo * 8;
+                float *red_p = red_w + jo * kCRedRow;
+                float2 h0[2][kCkptV2 + 1], h1[2][kCkptV2 + 1];
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch) {
+                    const float4 ck = half ? ck_hi[ch] : ck_lo[ch];
+                    h0[ch][0] = sw ? make_float2(ck.y, ck.x) : make_float2(ck.x, ck.y);
+                    h1[ch][0] = sw ? make_float2(ck.w, ck.z) : make_float2(ck.z, ck.w);
+                }
+#pragma unroll
+                for (int j = 0; j < kCkptV2; ++j) {   // forward sweep: re-derive the states of this half chunk
+                    const float4 dd = dd_p[j * NP];   // {dl0, dl0 u0, dl1, dl1 u1}
+                    const float4 B4 = bc_p[j * 8];
+                    const float2 B01 = make_float2(B4.x, B4.y), B23 = make_float2(B4.z, B4.w);
+#pragma unroll
+                    for (int ch = 0; ch < 2; ++ch) {
+                        const float2 dl2 = splat2(ch ? dd.z : dd.x), du2 = splat2(ch ? dd.w : dd.y);   // scalar-broadcast operands
+                        const float2 e0 = ex2_2(fmul2(dl2, A2[ch][0])), e1 = ex2_2(fmul2(dl2, A2[ch][1]));
+                        h0[ch][j + 1] = ffma2(e0, h0[ch][j], fmul2(du2, B01));
+                        h1[ch][j + 1] = ffma2(e1, h1[ch][j], fmul2(du2, B23));
+                    }
+                }
+                // slot loads of step j - 1 are issued before the stores of step j: neither nvcc nor ptxas moves an LDS above
+                // a (may-alias) STS, so in plain source order every step would wait out a full LDS latency
+                float4 dd_n = dd_p[(kCkptV2 - 1) * NP], B_n = bc_p[(kCkptV2 - 1) * 8], C_n = bc_p[(kCkptV2 - 1) * 8 + 4];
+                float2 dy_n = dy_p[(kCkptV2 - 1) * NP];
+#pragma unroll
+                for (int jb = kCkptV2 - 2; jb >= 0; jb -= 2) {
+                    float v[16];   // [kind (dB, dC)][step in group (2)][state in quad (4)], summed over the lane's two channels
+#pragma unroll
+                    for (int jj = 1; jj >= 0; --jj) {
+                        const int j = jb + jj;
+                        const float4 dd = dd_n, B4 = B_n, C4 = C_n;
+                        const float2 dyv = dy_n;
+                        if (j > 0) {
+                            dd_n = dd_p[(j - 1) * NP]; B_n = bc_p[(j - 1) * 8]; C_n = bc_p[(j - 1) * 8 + 4];
+                            dy_n = dy_p[(j - 1) * NP];
+                        }
+                        const float2 B01 = make_float2(B4.x, B4.y), B23 = make_float2(B4.z, B4.w);
+                        const float2 C01 = make_float2(C4.x, C4.y), C23 = make_float2(C4.z, C4.w);
+                        float2 dc0, dc1, db0, db1;
+                        float4 part;
+#pragma unroll
+                        for (int ch = 0; ch < 2; ++ch) {
+                            const float2 dl2 = splat2(ch ? dd.z : dd.x), du2 = splat2(ch ? dd.w : dd.y), dy2 = splat2(ch ? dyv.y : dyv.x);
+                            const float2 gg0 = ffma2(C01, dy2, G[ch][0]);   // g[t] = C dy + a[t+1] g[t+1]
+                            const float2 gg1 = ffma2(C23, dy2, G[ch][1]);
+                            if (ch == 0) {
+                                dc0 = fmul2(dy2, h0[ch][j + 1]); dc1 = fmul2(dy2, h1[ch][j + 1]);   // dC_t[n] += dy h[t]
+                                db0 = fmul2(gg0, du2); db1 = fmul2(gg1, du2);                       // dB_t[n] += g delta u
+                            } else {
+                                dc0 = ffma2(dy2, h0[ch][j + 1], dc0); dc1 = ffma2(dy2, h1[ch][j + 1], dc1);
+                                db0 = ffma2(gg0, du2, db0); db1 = ffma2(gg1, du2, db1);
+                            }
+                            const float2 sb = ffma2(gg1, B23, fmul2(gg0, B01));                      // sum_n g B
+                            // the decay factors are re-derived instead of living in 64 registers
+                            G[ch][0] = fmul2(ex2_2(fmul2(dl2, A2[ch][0])), gg0);                     // a[t] g[t]
+                            G[ch][1] = fmul2(ex2_2(fmul2(dl2, A2[ch][1])), gg1);
+                            const float2 w0 = fmul2(G[ch][0], h0[ch][j]), w1 = fmul2(G[ch][1], h1[ch][j]);   // (d a) a = g a h[t-1]
+                            const float2 sa = ffma2(w1, A2[ch][1], fmul2(w0, A2[ch][0]));            // sum_n (da a) A log2e
+                            dA[ch][0] = ffma2(w0, dl2, dA[ch][0]);                                   // dA[c,n] += (da a) delta
+                            dA[ch][1] = ffma2(w1, dl2, dA[ch][1]);
+                            if (ch == 0) { part.x = sb.x + sb.y; part.y = sa.x + sa.y; }
+                            else { part.z = sb.x + sb.y; part.w = sa.x + sa.y; }
+                        }
+                        s_w[j * (4 * SPL)] = part;
+                        v[4 * jj] = db0.x; v[4 * jj + 1] = db0.y; v[4 * jj + 2] = db1.x; v[4 * jj + 3] = db1.y;
+                        v[8 + 4 * jj] = dc0.x; v[8 + 4 * jj + 1] = dc0.y; v[8 + 4 * jj + 2] = dc1.x; v[8 + 4 * jj + 3] = dc1.y;
+                    }
+                    // reduce the 16 values over the 8 lanes that share this quad (lane bits 2, 3, 4)
+                    float r1[8];   // [kind][jj][m]: state 4 rq + 2 m + sw (odd pairs hold their state pairs swapped)
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) r1[m] = v[2 * m] + __shfl_xor_sync(0xffffffffu, v[2 * m + 1], 4);
+                    float r2[4];   // [kind][jj]: exchange on m
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        const float keep = up8 ? r1[2 * m + 1] : r1[2 * m];
+                        const float send = up8 ? r1[2 * m] : r1[2 * m + 1];
+                        r2[m] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                    }
+                    float r3[2];   // [kind]: exchange on jj
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) {
+                        const float keep = up16 ? r2[2 * m + 1] : r2[2 * m];
+                        const float send = up16 ? r2[2 * m] : r2[2 * m + 1];
+                        r3[m] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                    }
+                    *reinterpret_cast<float2 *>(red_p + jb * kCRedRow) = make_float2(r3[0], r3[1]);   // {dB, dC} of (step, state)
+                }
+
+                // ------------------------------------------------------------ phase C (this warp's 8 pairs x 8 steps)
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int tl = cr + 4 * q, t = jo + tl;
+                    if (tb + t < t1) {
+                        const float4 *sp4 = sS + (tl * 4) * SPL + cp;   // {S1, S2} of both channels, one plane per quad
+                        const float4 p0 = sp4[0], p1 = sp4[SPL], p2 = sp4[2 * SPL], p3 = sp4[3 * SPL];
+                        const float s1a = (p0.x + p1.x) + (p2.x + p3.x), s2a = ((p0.y + p1.y) + (p2.y + p3.y)) * kLn2;
+                        const float s1b = (p0.z + p1.z) + (p2.z + p3.z), s2b = ((p0.w + p1.w) + (p2.w + p3.w)) * kLn2;
+                        const float4 dd = sDD[t * NP + cp];
+                        const float2 dy = sDY[t * NP + cp];
+                        const float4 e4 = sEpi[t * NP + cp];
+                        const float draw0 = fmaf(s1a, e4.x, s2a) * e4.y, draw1 = fmaf(s1b, e4.z, s2b) * e4.w;   // d delta through softplus
+                        stg_pair<T>(dub + (int64_t)(tb + t) * p.du_rs, fmaf(dd.x, s1a, Dc.x * dy.x), fmaf(dd.z, s1b, Dc.y * dy.y), vec);
+                        stg_pair<T>(ddb + (int64_t)(tb + t) * p.dd_rs, draw0, draw1, vec);
+                        dD_acc.x = fmaf(dy.x, e4.x, dD_acc.x);
+                        dD_acc.y = fmaf(dy.y, e4.z, dD_acc.y);
+                        dbias_acc.x += draw0;
+                        dbias_acc.y += draw1;
+                    }
+                }
+                __syncwarp();   // the next half overwrites the partial planes
+            }
+
+            cp_async_wait<NST - 2>();
+            __syncthreads();   // (2) per-warp dB|dC rows complete; next chunk visible; this chunk's stage free
+            issue(i + NST);
+            if (i + 1 < nch) {   // next chunk's checkpoints travel while the row sums and phase A run
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch) {
+                    ck_lo[ch] = __ldcs(ckq + (size_t)(2 * (k - 1)) * ck_step + ch * (kNState / 4));
+                    ck_hi[ch] = __ldcs(ckq + (size_t)(2 * (k - 1) + 1) * ck_step + ch * (kNState / 4));
+                }
+            }
+            // dB|dC rows of this CTA: add the warps' tiles; row layout {dB[n], dC[n]} interleaved
+#pragma unroll
+            for (int q = 0; q < BCC; ++q) {
+                const int e = tid + q * NT, t = e >> 3, q8 = e & 7;
+                if (tb + t < t1) {
+                    const float4 *r = reinterpret_cast<const float4 *>(sRed + t * kCRedRow) + q8;
+                    constexpr int W4 = kChunk * kCRedRow / 4;
+                    float4 acc = r[0];
+#pragma unroll
+                    for (int w = 1; w < NW; ++w) {
+                        const float4 x = r[w * W4];
+                        acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+                    }
+                    __stcs(reinterpret_cast<float4 *>(p.part_bc + (((size_t)blk * p.B + b) * p.L + tb + t) * 32) + q8, acc);
+                }
+            }
+            if (i + 1 < nch) phase_a(i + 1);
+        }
+
+        // ---- end of unit: parameter-gradient partials, carry-out ----
+        {
+            float *dst = p.part_par + ((size_t)(b * cs.nseg + seg) * 18) * p.ED + c0 + 2 * rp;
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                dst[(size_t)(4 * rq + sw) * p.ED + ch] = dA[ch][0].x;
+                dst[(size_t)(4 * rq + 1 - sw) * p.ED + ch] = dA[ch][0].y;
+                dst[(size_t)(4 * rq + 2 + sw) * p.ED + ch] = dA[ch][1].x;
+                dst[(size_t)(4 * rq + 3 - sw) * p.ED + ch] = dA[ch][1].y;
+            }
+        }
+        // dD, ddt_bias: add the four item rows (cr) of each pair inside the warp
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {
+            dD_acc.x += __shfl_xor_sync(0xffffffffu, dD_acc.x, o);
+            dD_acc.y += __shfl_xor_sync(0xffffffffu, dD_acc.y, o);
+            dbias_acc.x += __shfl_xor_sync(0xffffffffu, dbias_acc.x, o);
+            dbias_acc.y += __shfl_xor_sync(0xffffffffu, dbias_acc.y, o);
+        }
+        if (cr == 0) {
+            float *dst = p.part_par + ((size_t)(b * cs.nseg + seg) * 18) * p.ED + c0 + 2 * cp;
+            *reinterpret_cast<float2 *>(dst + (size_t)16 * p.ED) = dD_acc;
+            *reinterpret_cast<float2 *>(dst + (size_t)17 * p.ED) = dbias_acc;
+        }
+        if (seg > 0) {
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                const float4 gv = sw ? make_float4(G[ch][0].y, G[ch][0].x, G[ch][1].y, G[ch][1].x)
+                                     : make_float4(G[ch][0].x, G[ch][0].y, G[ch][1].x, G[ch][1].y);
+                __stcg(reinterpret_cast<float4 *>(carry + ch * kNState), gv);
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) st_release(cs.flags + unit, 1);
+        }
+        cp_async_wait<0>();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- host
+struct BwdWs {
+    size_t part_bc, part_par, total;
+};
+static BwdWs bwd_ws(int B, int L, int ED) {
+    int cpc, nblk, nseg, seg_len;
+    chain_bwd_plan(B, L, ED, cpc, nblk, nseg, seg_len);
+    BwdWs w{};
+    size_t off = chain_bytes(B, ED, nblk, nseg);
+    w.part_bc = off;
+    off += align_up((size_t)nblk * B * L * 32 * sizeof(float), 256);
+    w.part_par = off;
+    off += align_up((size_t)B * nseg * 18 * ED * sizeof(float), 256);
+    w.total = off;
+    return w;
+}
+
+size_t chain_bwd_workspace_bytes(int B, int L, int ED) { return bwd_ws(B, L, ED).total; }
+
+template <typename T, bool HAS_Z, int CPB, int CPC>
+static void launch_bwd_chain_inst(const ScanParams &p, const ChainSched &cs, cudaStream_t st) {
+    constexpr size_t smem = BwdChainSmem<T, HAS_Z, CPC>::kTotal;
+    const int grid = persistent_grid<selscan_bwd_chain_kernel<T, HAS_Z, CPB, CPC>>(2 * CPC, smem, cs.total);
+    selscan_bwd_chain_kernel<T, HAS_Z, CPB, CPC><<<grid, 2 * CPC, smem, st>>>(p, cs);
+}
+
+template <typename T, int CPC>
+static void launch_bwd_chain_cpc(const ScanParams &p, const ChainSched &cs, bool has_z, int cpb, cudaStream_t st) {
+    if (has_z) {
+        if (cpb == 16) launch_bwd_chain_inst<T, true, 16, CPC>(p, cs, st);
+        else launch_bwd_chain_inst<T, true, 0, CPC>(p, cs, st);
+    } else {
+        if (cpb == 16) launch_bwd_chain_inst<T, false, 16, CPC>(p, cs, st);
+        else launch_bwd_chain_inst<T, false, 0, CPC>(p, cs, st);
+    }
+}
+
+template <typename T>
+static int launch_bwd_chain_t(const gfe_selscan_args *a, cudaStream_t st) {
+    int cpc, nblk, nseg, seg_len;
+    chain_bwd_plan(a->batch, a->seqlen, a->d_inner, cpc, nblk, nseg, seg_len);
+    const BwdWs w = bwd_ws(a->batch, a->seqlen, a->d_inner);
+    if (a->ws == nullptr || a->ws_bytes < w.total) {
+        set_error("selscan_bwd: workspace too small (%zu < %zu)", a->ws ? a->ws_bytes : (size_t)0, w.total);
+        return GFE_ERR_WORKSPACE;
+    }
+    int rc = chain_check_alignment(a);
+    if (rc != GFE_OK) return rc;
+    ScanParams p{};
+    chain_fill_params(p, a);
+    char *ws = reinterpret_cast<char *>(a->ws);
+    p.part_bc = reinterpret_cast<float *>(ws + w.part_bc);
+    p.part_par = reinterpret_cast<float *>(ws + w.part_par);
+    p.dout = a->dout; p.do_bs = a->dout_bs; p.do_rs = a->dout_rs;
+    p.du = a->du; p.du_bs = a->du_bs; p.du_rs = a->du_rs;
+    p.ddelta = a->ddelta; p.dd_bs = a->ddelta_bs; p.dd_rs = a->ddelta_rs;
+    p.dz = a->dz; p.dz_bs = a->dz_bs; p.dz_rs = a->dz_rs;
+    p.dBm = a->dBm; p.dB_bs = a->dB_bs; p.dB_rs = a->dB_rs;
+    p.dCm = a->dCm; p.dC_bs = a->dC_bs; p.dC_rs = a->dC_rs;
+    p.dA_log = a->dA_log; p.dD = a->dD; p.ddt_bias = a->ddt_bias;
+    p.nseg = nseg;   // finalize_par sums over B * nseg partial rows
+    p.G = nblk;      // finalize_bc sums one row per channel block
+    p.bc_interleaved = 1;
+    ChainSched cs{};
+    rc = chain_fill_sched(cs, ws, a->batch, a->d_inner, nblk, nseg, seg_len, st);
+    if (rc != GFE_OK) return rc;
+    const int cpb = chain_cpb(a, true);
+    if (chain_pair_stores(a, true)) p.flags |= kFlagPairStores;
+    {
+        ScopedKernelTimer tm(K_SELSCAN_BWD, st);
+        const bool hz = a->z != nullptr;
+        if (cpc == 64) launch_bwd_chain_cpc<T, 64>(p, cs, hz, cpb, st);
+        else if (cpc == 32) launch_bwd_chain_cpc<T, 32>(p, cs, hz, cpb, st);
+        else launch_bwd_chain_cpc<T, 16>(p, cs, hz, cpb, st);
+    }
+    rc = check_launch("selscan_bwd (chained)");
+    if (rc != GFE_OK) return rc;
+    launch_bwd_finalize(a, p, st, rc);
+    return rc;
+}
+
+int chain_launch_bwd(const gfe_selscan_args *a, cudaStream_t st) {
+    switch (a->dtype) {
+        case GFE_F32: return launch_bwd_chain_t<float>(a, st);
+        case GFE_BF16: return launch_bwd_chain_t<__nv_bfloat16>(a, st);
+        default: return launch_bwd_chain_t<__half>(a, st);
+    }
+}
+
+}  // namespace gfe

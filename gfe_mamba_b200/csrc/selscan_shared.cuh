@@ -235,11 +235,42 @@ __device__ __forceinline__ void stage_tile1(unsigned char *dst, const T *src, in
 }
 #endif  // __CUDACC__
 
-// host side (selscan_v2_*.cu)
-bool v2_applicable(int B, int L, int ED);                 // shape-only: both directions take the same decision
-size_t v2_fwd_workspace_bytes(int B, int L, int ED);
-size_t v2_bwd_workspace_bytes(int B, int L, int ED);
-int v2_launch_fwd(const gfe_selscan_args *a, cudaStream_t st);
-int v2_launch_bwd(const gfe_selscan_args *a, cudaStream_t st);
+// Grid of a persistent kernel: min(total units, resident CTAs of the CURRENT device).  The dynamic-shared-memory opt-in
+// is a per-device attribute and the occupancy depends on the device, so both are cached per (kernel, device).
+#ifdef __CUDACC__
+template <auto Kernel>
+static int persistent_grid(int nt, size_t smem, int total) {
+    constexpr int kMaxDev = 64;
+    static int slots_of[kMaxDev];   // 0 = not asked yet (benign race: every thread computes the same value)
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); dev = 0; }
+    int slots = (dev >= 0 && dev < kMaxDev) ? slots_of[dev] : 0;
+    if (slots == 0) {
+        int per_sm = 0;
+        cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, Kernel, nt, smem) != cudaSuccess || per_sm < 1) {
+            (void)cudaGetLastError();
+            per_sm = 1;
+        }
+        slots = sm_count() * per_sm;
+        if (dev >= 0 && dev < kMaxDev) slots_of[dev] = slots;
+    }
+    return total < slots ? total : slots;
+}
+#endif
+
+// host side of the chained kernels (selscan_chain_host.cu, selscan_chain_bwd.cu)
+#ifndef GFE_FWD_CPC_DEFAULT
+#define GFE_FWD_CPC_DEFAULT 64   // channel-block width of the forward kernel when ED allows it
+#endif
+#ifndef GFE_BWD_CPC_DEFAULT
+#define GFE_BWD_CPC_DEFAULT 64
+#endif
+bool chain_applicable(int B, int L, int ED);              // shape-only: both directions take the same decision
+size_t chain_ckpt_state_bytes(int B, int L, int ED);
+size_t chain_fwd_workspace_bytes(int B, int L, int ED);
+size_t chain_bwd_workspace_bytes(int B, int L, int ED);
+int chain_launch_fwd(const gfe_selscan_args *a, cudaStream_t st);
+int chain_launch_bwd(const gfe_selscan_args *a, cudaStream_t st);
 
 }  // namespace gfe

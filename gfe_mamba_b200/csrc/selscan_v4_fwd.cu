@@ -18,8 +18,8 @@
 
 namespace gfe {
 
-constexpr int kV4CPC = 64;            // channels per CTA
-constexpr int kV4NT = 2 * kV4CPC;     // 128 threads: lane (pair, quad) owns 2 channels x 4 states
+// CPC = channels per CTA (64, 32 or 16); 2 * CPC threads: lane (pair, quad) owns 2 channels x 4 states.  With CPC = 16 a
+// CTA is a single warp and every __syncthreads below is a warp barrier: the warps of an SM then run fully decoupled.
 #ifndef GFE_SOFTPLUS2
 #define GFE_SOFTPLUS2 1
 #endif
@@ -32,10 +32,10 @@ constexpr int kV4NT = 2 * kV4CPC;     // 128 threads: lane (pair, quad) owns 2 c
 #ifndef GFE_V4_MINB
 #define GFE_V4_MINB 3
 #endif
-constexpr int kV4YPlane = 36;         // float2 per (t, quad) plane of the partial C.h: 32 pairs + 32 B skew (conflict-free STS.64)
-
-template <typename T, bool HAS_Z>
+template <typename T, bool HAS_Z, int CPC>
 struct FwdV4Smem {
+    static constexpr int kV4CPC = CPC;
+    static constexpr int kYPlane = CPC / 2 + 4;   // float2 per (t, quad) plane of the partial C.h: CPC / 2 pairs + 32 B skew (conflict-free STS.64)
     static constexpr int kStages = sizeof(T) == 4 ? 2 : 3;
     static constexpr int kNTile = HAS_Z ? 3 : 2;
     static constexpr int kTile = kChunk * kV4CPC * (int)sizeof(T);      // one of u, delta, z
@@ -44,16 +44,17 @@ struct FwdV4Smem {
     static constexpr int kOffDD = kStages * kStage;                      // float2 [16][64] {dl, dl*u}
     static constexpr int kOffBC = kOffDD + kChunk * kV4CPC * 8;          // float4 [16][8]  B quads | C quads
     static constexpr int kOffY = kOffBC + kChunk * 8 * 16;               // float2 [16][4][36] partial C.h of a channel pair
-    static constexpr int kTotal = kOffY + kChunk * 4 * kV4YPlane * 8;
+    static constexpr int kTotal = kOffY + kChunk * 4 * kYPlane * 8;
 };
 
 // The 16 recurrence steps of one chunk, with the slot loads software-pipelined by hand: neither nvcc nor ptxas moves the
 // three LDS of step j + 1 above the partial-sum STS of step j (may-alias shared addresses; __restrict__ does not reach
 // ptxas), so in source order every step waited out a full LDS latency before its first FMUL2 (seen in the SASS).
+template <int CPC>
 __device__ __forceinline__ void v4_recur_chunk(const float4 *__restrict__ dd_r, const float4 *__restrict__ bc_r,
                                                float2 *__restrict__ y_w, const float2 (&A2)[2][2], float2 (&h)[2][2],
                                                float4 *__restrict__ ckq, size_t ck_step, int tb, int t1) {
-    constexpr int CPC = kV4CPC;
+    constexpr int kV4YPlane = CPC / 2 + 4;
     constexpr int PF = GFE_V4_PREFETCH;   // slot loads are issued PF steps ahead of their use, BEFORE the stores of the steps between
     float4 dd_q[PF + 1], B_q[PF + 1], C_q[PF + 1];
 #pragma unroll
@@ -92,18 +93,19 @@ __device__ __forceinline__ void v4_recur_chunk(const float4 *__restrict__ dd_r, 
     }
 }
 
-template <typename T, bool HAS_Z, int CPB>
-__global__ void __launch_bounds__(kV4NT, GFE_V4_MINB) selscan_fwd_v4_kernel(ScanParams p, ChainSched cs) {
+template <typename T, bool HAS_Z, int CPB, int CPC>
+__global__ void __launch_bounds__(2 * CPC, GFE_V4_MINB * (64 / CPC)) selscan_fwd_v4_kernel(ScanParams p, ChainSched cs) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_unit;
-    using SM = FwdV4Smem<T, HAS_Z>;
-    constexpr int NT = kV4NT, CPC = kV4CPC, NST = SM::kStages, NTILE = SM::kNTile;
+    using SM = FwdV4Smem<T, HAS_Z, CPC>;
+    constexpr int NT = 2 * CPC, NP = CPC / 2, NST = SM::kStages, NTILE = SM::kNTile;
+    constexpr int kV4YPlane = SM::kYPlane;
     constexpr int RB = CPC * (int)sizeof(T);          // bytes per tile row
     constexpr int PPT = kChunk * RB / 16 / NT;        // 16-byte pieces per thread per activation tile (1 bf16, 2 fp32)
     constexpr int BCP = kChunk * kNState * (int)sizeof(T) / 16;   // pieces per B (or C) tile: 32 bf16, 64 fp32
     const int tid = threadIdx.x;
     const int rp = tid >> 2, rq = tid & 3;     // recurrence mapping: channel pair in block (0..31), state quad
-    const int ip = tid & 31, ir = tid >> 5;    // item mapping: channel pair, rows ir + 4 i
+    const int ip = tid % NP, ir = tid / NP;    // item mapping: channel pair, rows ir + 4 i
 
     float4 *sDD = reinterpret_cast<float4 *>(smem + SM::kOffDD);   // [t][pair] {dl0, dl0*u0, dl1, dl1*u1}
     float4 *sBC = reinterpret_cast<float4 *>(smem + SM::kOffBC);
@@ -118,9 +120,7 @@ __global__ void __launch_bounds__(kV4NT, GFE_V4_MINB) selscan_fwd_v4_kernel(Scan
 
     // staging geometry of this thread (fixed): activation tiles and B|C tiles
     const int srow = (tid * PPT) / (RB / 16), spiece = (tid * PPT) % (RB / 16);   // PPT consecutive pieces of one row
-    const bool bc_thread = tid < 2 * BCP;
-    const int bcsel = tid / BCP;                                      // 0: B, 1: C
-    const int bcrow = (tid % BCP) / (BCP / kChunk), bcpiece = (tid % BCP) % (BCP / kChunk);
+    constexpr int BCI = (2 * BCP + NT - 1) / NT;   // B|C pieces per thread: piece i of this thread is tid + i * NT of [B pieces | C pieces]
 
     for (;;) {
         __syncthreads();   // every thread is done with the previous unit's shared memory
@@ -148,8 +148,9 @@ __global__ void __launch_bounds__(kV4NT, GFE_V4_MINB) selscan_fwd_v4_kernel(Scan
         const size_t ck_step = (size_t)p.ED * (kNState / 4);
 
         // per-thread source pointers of the staged pieces at row t0 (advanced by 16 rows per chunk)
-        const char *su, *sd, *sz = nullptr, *sbc = nullptr;
-        int64_t adv_u, adv_d, adv_z = 0, adv_bc = 0;
+        const char *su, *sd, *sz = nullptr, *sbc[BCI];
+        int64_t adv_u, adv_d, adv_z = 0, adv_bc[BCI];
+        int bcrow[BCI];
         if constexpr (CPB == 16) {
             su = reinterpret_cast<const char *>(ub + (int64_t)(t0 + srow) * p.u_rs) + spiece * 16;
             sd = reinterpret_cast<const char *>(db + (int64_t)(t0 + srow) * p.d_rs) + spiece * 16;
@@ -159,14 +160,18 @@ __global__ void __launch_bounds__(kV4NT, GFE_V4_MINB) selscan_fwd_v4_kernel(Scan
                 sz = reinterpret_cast<const char *>(zb + (int64_t)(t0 + srow) * p.z_rs) + spiece * 16;
                 adv_z = (int64_t)kChunk * p.z_rs * (int64_t)sizeof(T);
             }
-            if (bc_thread) {
-                const int64_t rs = bcsel ? p.C_rs : p.B_rs;
-                sbc = reinterpret_cast<const char *>((bcsel ? Cb : Bb) + (int64_t)(t0 + bcrow) * rs) + bcpiece * 16;
-                adv_bc = (int64_t)kChunk * rs * (int64_t)sizeof(T);
+#pragma unroll
+            for (int i = 0; i < BCI; ++i) {
+                const int pc = tid + i * NT;                    // < 2 * BCP checked at issue time
+                const int sel = pc / BCP, within = pc % BCP;    // 0: B, 1: C
+                bcrow[i] = within / (BCP / kChunk);
+                const int64_t rs = sel ? p.C_rs : p.B_rs;
+                sbc[i] = reinterpret_cast<const char *>((sel ? Cb : Bb) + (int64_t)(t0 + bcrow[i]) * rs) + (within % (BCP / kChunk)) * 16;
+                adv_bc[i] = (int64_t)kChunk * rs * (int64_t)sizeof(T);
             }
         }
         const uint32_t dst_act = smem_u32(smem) + srow * RB + spiece * 16;
-        const uint32_t dst_bc = smem_u32(smem) + NTILE * SM::kTile + bcsel * SM::kBCRaw + (tid % BCP) * 16;
+        const uint32_t dst_bc = smem_u32(smem) + NTILE * SM::kTile + tid * 16;   // the raw B tile is followed by the raw C tile
 
         auto issue = [&](int k) {   // chunk k of this segment -> stage k % NST
             if (k < nch) {
@@ -182,7 +187,9 @@ __global__ void __launch_bounds__(kV4NT, GFE_V4_MINB) selscan_fwd_v4_kernel(Scan
                             if (HAS_Z) cp_async<16>(dst_act + so + 2 * SM::kTile + i * 16, sz + (int64_t)k * adv_z + i * 16);
                         }
                     }
-                    if (bc_thread && bcrow < nrows) cp_async<16>(dst_bc + so, sbc + (int64_t)k * adv_bc);
+#pragma unroll
+                    for (int i = 0; i < BCI; ++i)
+                        if (tid + i * NT < 2 * BCP && bcrow[i] < nrows) cp_async<16>(dst_bc + so + i * NT * 16, sbc[i] + (int64_t)k * adv_bc[i]);
                 } else {
                     unsigned char *s = smem + so;
                     stage_tile<T, 0, CPC, NT>(s, ub + (int64_t)tb * p.u_rs, p.u_rs, nrows, tid);
@@ -265,13 +272,16 @@ __global__ void __launch_bounds__(kV4NT, GFE_V4_MINB) selscan_fwd_v4_kernel(Scan
                 uq[i] = lds_pair(sU + (ir + 4 * i) * CPC, ip);
                 if (HAS_Z) zq[i] = lds_pair(sZ + (ir + 4 * i) * CPC, ip);
             }
-            float4 bcv = make_float4(0.f, 0.f, 0.f, 0.f);
-            {   // B|C rows -> fp32 quads: [t][B quads 0..3 | C quads 0..3]; 128 threads = 16 rows x 8 quads
-                const int t = tid >> 3, q8 = tid & 7;
+            constexpr int BCC = kChunk * 8 / NT;   // fp32 quads this thread converts (16 rows x 8 quads over the CTA)
+            float4 bcv[BCC];
+#pragma unroll
+            for (int i = 0; i < BCC; ++i) {   // B|C rows -> fp32 quads: [t][B quads 0..3 | C quads 0..3]
+                const int e = tid + i * NT, t = e >> 3, q8 = e & 7;
+                bcv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (tb + t < t1) {
                     const T *src = sBr + (q8 < 4 ? 0 : kChunk * 16) + t * 16 + 4 * (q8 & 3);
                     const float2 lo = lds_pair(src, 0), hi = lds_pair(src, 1);
-                    bcv = make_float4(lo.x, lo.y, hi.x, hi.y);
+                    bcv[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
                 }
             }
 #pragma unroll
@@ -281,14 +291,15 @@ __global__ void __launch_bounds__(kV4NT, GFE_V4_MINB) selscan_fwd_v4_kernel(Scan
                 const float2 u2 = uq[i];
                 const float u0 = valid ? u2.x : 0.f, u1 = valid ? u2.y : 0.f;
                 const float dl0 = valid ? dl[2 * i] : 0.f, dl1 = valid ? dl[2 * i + 1] : 0.f;   // padded step: a = 1, bx = 0
-                sDD[t * (CPC / 2) + ip] = make_float4(dl0, dl0 * u0, dl1, dl1 * u1);
+                sDD[t * NP + ip] = make_float4(dl0, dl0 * u0, dl1, dl1 * u1);
                 Du[i] = make_float2(Dc.x * u0, Dc.y * u1);
                 if (HAS_Z) {
                     const float2 z2 = zq[i];
                     gate[i] = make_float2(z2.x * sigmoid_fast(z2.x), z2.y * sigmoid_fast(z2.y));
                 }
             }
-            sBC[tid] = bcv;
+#pragma unroll
+            for (int i = 0; i < BCC; ++i) sBC[tid + i * NT] = bcv[i];
         };
 
         cp_async_wait<NST - 1>();
@@ -298,7 +309,7 @@ __global__ void __launch_bounds__(kV4NT, GFE_V4_MINB) selscan_fwd_v4_kernel(Scan
         for (int k = 0; k < nch; ++k) {
             const int tb = t0 + k * kChunk;
             __syncthreads();   // (1) slots of chunk k are complete
-            v4_recur_chunk(dd_r, bc_r, y_w, A2, h, ckq, ck_step, tb, t1);   // 16 steps of this lane's 2 x 4 states
+            v4_recur_chunk<CPC>(dd_r, bc_r, y_w, A2, h, ckq, ck_step, tb, t1);   // 16 steps of this lane's 2 x 4 states
             cp_async_wait<NST - 2>();   // chunk k + 1 has landed (this thread's pieces)
             __syncthreads();            // (2) partial sums complete; chunk k + 1 visible; stage k % NST free
             issue(k + NST);
@@ -341,38 +352,33 @@ __global__ void __launch_bounds__(kV4NT, GFE_V4_MINB) selscan_fwd_v4_kernel(Scan
 }
 
 // ---------------------------------------------------------------------------------------------------- host
-template <typename T, bool HAS_Z, int CPB>
+template <typename T, bool HAS_Z, int CPB, int CPC>
 static void launch_fwd_v4_inst(const ScanParams &p, const ChainSched &cs, cudaStream_t st) {
-    auto kernel = selscan_fwd_v4_kernel<T, HAS_Z, CPB>;
-    constexpr size_t smem = FwdV4Smem<T, HAS_Z>::kTotal;
-    static thread_local int cache_total = -1, cache_grid = 0;
-    if (cache_total != cs.total) {
-        int per_sm = 0;
-        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kV4NT, smem) != cudaSuccess || per_sm < 1) {
-            (void)cudaGetLastError();
-            per_sm = 1;
-        }
-        const int64_t slots = (int64_t)sm_count() * per_sm;
-        cache_grid = (int)(cs.total < slots ? cs.total : slots);
-        cache_total = cs.total;
-    }
-    kernel<<<cache_grid, kV4NT, smem, st>>>(p, cs);
+    constexpr size_t smem = FwdV4Smem<T, HAS_Z, CPC>::kTotal;
+    const int grid = persistent_grid<selscan_fwd_v4_kernel<T, HAS_Z, CPB, CPC>>(2 * CPC, smem, cs.total);
+    selscan_fwd_v4_kernel<T, HAS_Z, CPB, CPC><<<grid, 2 * CPC, smem, st>>>(p, cs);
 }
 
-// called by launch_fwd_v2_t when the channel block is 64 wide: same plan, same workspace, same checkpoints
-template <typename T>
-void v4_launch_fwd_kernel(const ScanParams &p, const ChainSched &cs, bool has_z, int cpb, cudaStream_t st) {
+template <typename T, int CPC>
+static void launch_fwd_v4_cpc(const ScanParams &p, const ChainSched &cs, bool has_z, int cpb, cudaStream_t st) {
     if (has_z) {
-        if (cpb == 16) launch_fwd_v4_inst<T, true, 16>(p, cs, st);
-        else launch_fwd_v4_inst<T, true, 0>(p, cs, st);
+        if (cpb == 16) launch_fwd_v4_inst<T, true, 16, CPC>(p, cs, st);
+        else launch_fwd_v4_inst<T, true, 0, CPC>(p, cs, st);
     } else {
-        if (cpb == 16) launch_fwd_v4_inst<T, false, 16>(p, cs, st);
-        else launch_fwd_v4_inst<T, false, 0>(p, cs, st);
+        if (cpb == 16) launch_fwd_v4_inst<T, false, 16, CPC>(p, cs, st);
+        else launch_fwd_v4_inst<T, false, 0, CPC>(p, cs, st);
     }
 }
-template void v4_launch_fwd_kernel<float>(const ScanParams &, const ChainSched &, bool, int, cudaStream_t);
-template void v4_launch_fwd_kernel<__nv_bfloat16>(const ScanParams &, const ChainSched &, bool, int, cudaStream_t);
-template void v4_launch_fwd_kernel<__half>(const ScanParams &, const ChainSched &, bool, int, cudaStream_t);
+
+// called by the chained-kernel dispatch (selscan_v2_fwd.cu) with cpc = cs.nblk's channel-block width
+template <typename T>
+void v4_launch_fwd_kernel(const ScanParams &p, const ChainSched &cs, int cpc, bool has_z, int cpb, cudaStream_t st) {
+    if (cpc == 64) launch_fwd_v4_cpc<T, 64>(p, cs, has_z, cpb, st);
+    else if (cpc == 32) launch_fwd_v4_cpc<T, 32>(p, cs, has_z, cpb, st);
+    else launch_fwd_v4_cpc<T, 16>(p, cs, has_z, cpb, st);
+}
+template void v4_launch_fwd_kernel<float>(const ScanParams &, const ChainSched &, int, bool, int, cudaStream_t);
+template void v4_launch_fwd_kernel<__nv_bfloat16>(const ScanParams &, const ChainSched &, int, bool, int, cudaStream_t);
+template void v4_launch_fwd_kernel<__half>(const ScanParams &, const ChainSched &, int, bool, int, cudaStream_t);
 
 }  // namespace gfe
