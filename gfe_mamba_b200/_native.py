@@ -54,6 +54,7 @@ SIGNATURES = {
     "gfe_pscan_fwd": (ctypes.c_int, [c_vp, c_vp, c_vp] + [ctypes.c_int] * 4 + [c_vp, c_sz, c_vp]),
     "gfe_pscan_bwd": (ctypes.c_int, [c_vp] * 5 + [ctypes.c_int] * 4 + [c_vp, c_sz, c_vp]),
     "gfe_selscan_ckpt_bytes": (c_sz, [ctypes.c_int] * 4),
+    "gfe_selscan_ckpt_bytes_dt": (c_sz, [ctypes.c_int] * 5),
     "gfe_selscan_fwd_workspace_bytes": (c_sz, [ctypes.c_int] * 4),
     "gfe_selscan_bwd_workspace_bytes": (c_sz, [ctypes.c_int] * 4),
     "gfe_selscan_fwd": (ctypes.c_int, [ctypes.POINTER(SelscanArgs), c_vp]),
@@ -68,6 +69,8 @@ SIGNATURES = {
     "gfe_add_rmsnorm_fwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_float, ctypes.c_int, c_vp]),
     "gfe_add_rmsnorm_bwd_workspace_bytes": (c_sz, [c_i64, ctypes.c_int]),
     "gfe_add_rmsnorm_bwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_int, c_vp, c_sz, c_vp]),
+    "gfe_clip_adam_chunk_elems": (ctypes.c_int, []),
+    "gfe_clip_adam_step": (ctypes.c_int, [c_vp] * 11 + [ctypes.c_int] * 2 + [ctypes.c_float] * 5 + [ctypes.c_int] * 2 + [c_vp]),
     "gfe_timing_enable": (ctypes.c_int, [ctypes.c_int]),
     "gfe_timing_kernel_count": (ctypes.c_int, []),
     "gfe_timing_kernel_name": (ctypes.c_char_p, [ctypes.c_int]),

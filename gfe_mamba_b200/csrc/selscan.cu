@@ -694,9 +694,9 @@ static int validate_common(const gfe_selscan_args *a, bool bwd) {
         if ((a->z != nullptr) != (a->dz != nullptr)) { set_error("selscan_bwd: dz must be given iff z is"); return GFE_ERR_ARG; }
         if (!a->ckpt) { set_error("selscan_bwd: checkpoints from the forward pass are required"); return GFE_ERR_WORKSPACE; }
     }
-    if (a->ckpt && a->ckpt_bytes < gfe_selscan_ckpt_bytes(a->batch, a->seqlen, a->d_inner, a->d_state)) {
+    if (a->ckpt && a->ckpt_bytes < gfe_selscan_ckpt_bytes_dt(a->batch, a->seqlen, a->d_inner, a->d_state, a->dtype)) {
         set_error("selscan: checkpoint buffer too small (%zu < %zu)", a->ckpt_bytes,
-                  gfe_selscan_ckpt_bytes(a->batch, a->seqlen, a->d_inner, a->d_state));
+                  gfe_selscan_ckpt_bytes_dt(a->batch, a->seqlen, a->d_inner, a->d_state, a->dtype));
         return GFE_ERR_WORKSPACE;
     }
     if (a->ckpt && (reinterpret_cast<uintptr_t>(a->ckpt) & 7) != 0) { set_error("selscan: ckpt must be 8-byte aligned"); return GFE_ERR_ARG; }
@@ -867,12 +867,17 @@ static int launch_bwd(const gfe_selscan_args *a, cudaStream_t st) {
 
 extern "C" {
 
-GFE_API size_t gfe_selscan_ckpt_bytes(int B, int L, int ED, int N) {
+GFE_API size_t gfe_selscan_ckpt_bytes_dt(int B, int L, int ED, int N, int dtype) {
     if (B <= 0 || L <= 0 || ED <= 0 || N != gfe::kNState) return 0;
-    // chunk-start states (fp32) + y before the gate (up to 4 bytes per element)
-    if (gfe::chain_applicable(B, L, ED))
-        return (size_t)B * ((L + gfe::kCkptV2 - 1) / gfe::kCkptV2) * ED * gfe::kNState * sizeof(float) + (size_t)B * L * ED * sizeof(float);
-    return gfe::ckpt_state_bytes(B, L, ED) + (size_t)B * L * ED * sizeof(float);
+    if (dtype != GFE_F32 && dtype != GFE_BF16 && dtype != GFE_F16) return 0;
+    // segment-start states (fp32) + y before the gate in the activation dtype
+    const size_t ybytes = (size_t)B * L * ED * (dtype == GFE_F32 ? 4 : 2);
+    if (gfe::chain_applicable(B, L, ED)) return gfe::chain_ckpt_state_bytes(B, L, ED) + ybytes;
+    return gfe::ckpt_state_bytes(B, L, ED) + ybytes;
+}
+
+GFE_API size_t gfe_selscan_ckpt_bytes(int B, int L, int ED, int N) {   // upper bound over the activation dtypes
+    return gfe_selscan_ckpt_bytes_dt(B, L, ED, N, GFE_F32);
 }
 
 GFE_API size_t gfe_selscan_fwd_workspace_bytes(int B, int L, int ED, int N) {

@@ -34,9 +34,6 @@ bool chain_pair_stores(const gfe_selscan_args *a, bool bwd);
 int chain_check_alignment(const gfe_selscan_args *a);
 void launch_bwd_finalize(const gfe_selscan_args *a, ScanParams &p, cudaStream_t st, int &rc);   // selscan.cu
 
-#ifndef GFE_CBWD_MINB
-#define GFE_CBWD_MINB 3        // CTAs of 128 threads per SM the register budget is set for (168 registers)
-#endif
 constexpr int kCRedRow = 36;   // padded row (floats) of the per-warp dB|dC tile: [t][n]{dB, dC}
 constexpr int kCBCPlane = kChunk * 8 + 4;   // float4 per B|C plane; the 64 B skew keeps the natural and the pair-swapped plane
                                             // (read by the even / odd pairs of one quarter-warp) on disjoint banks
@@ -325,6 +322,9 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
                 const float4 *bc_p = bc_r + jo * 8;
                 float *red_p = red_w + jo * kCRedRow;
                 float2 h0[2][kCkptV2 + 1], h1[2][kCkptV2 + 1];
+#if GFE_CBWD_KEEP_A
+                float2 e0h[2][kCkptV2], e1h[2][kCkptV2];
+#endif
 #pragma unroll
                 for (int ch = 0; ch < 2; ++ch) {
                     const float4 ck = half ? ck_hi[ch] : ck_lo[ch];
@@ -340,6 +340,9 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
                     for (int ch = 0; ch < 2; ++ch) {
                         const float2 dl2 = splat2(ch ? dd.z : dd.x), du2 = splat2(ch ? dd.w : dd.y);   // scalar-broadcast operands
                         const float2 e0 = ex2_2(fmul2(dl2, A2[ch][0])), e1 = ex2_2(fmul2(dl2, A2[ch][1]));
+#if GFE_CBWD_KEEP_A
+                        e0h[ch][j] = e0; e1h[ch][j] = e1;
+#endif
                         h0[ch][j + 1] = ffma2(e0, h0[ch][j], fmul2(du2, B01));
                         h1[ch][j + 1] = ffma2(e1, h1[ch][j], fmul2(du2, B23));
                     }
@@ -377,9 +380,13 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
                                 db0 = ffma2(gg0, du2, db0); db1 = ffma2(gg1, du2, db1);
                             }
                             const float2 sb = ffma2(gg1, B23, fmul2(gg0, B01));                      // sum_n g B
-                            // the decay factors are re-derived instead of living in 64 registers
+#if GFE_CBWD_KEEP_A
+                            G[ch][0] = fmul2(e0h[ch][j], gg0);                                       // a[t] g[t]
+                            G[ch][1] = fmul2(e1h[ch][j], gg1);
+#else                       // the decay factors are re-derived instead of living in 64 registers
                             G[ch][0] = fmul2(ex2_2(fmul2(dl2, A2[ch][0])), gg0);                     // a[t] g[t]
                             G[ch][1] = fmul2(ex2_2(fmul2(dl2, A2[ch][1])), gg1);
+#endif
                             const float2 w0 = fmul2(G[ch][0], h0[ch][j]), w1 = fmul2(G[ch][1], h1[ch][j]);   // (d a) a = g a h[t-1]
                             const float2 sa = ffma2(w1, A2[ch][1], fmul2(w0, A2[ch][0]));            // sum_n (da a) A log2e
                             dA[ch][0] = ffma2(w0, dl2, dA[ch][0]);                                   // dA[c,n] += (da a) delta

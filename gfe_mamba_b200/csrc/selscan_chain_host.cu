@@ -54,7 +54,7 @@ void chain_fwd_plan(int B, int L, int ED, int &cpc, int &nblk, int &nseg, int &s
 void chain_bwd_plan(int B, int L, int ED, int &cpc, int &nblk, int &nseg, int &seg_len) {
     cpc = bwd_cpc(ED);
     nblk = ED / cpc;
-    chain_plan(B, L, nblk, 3 * (64 / cpc), nseg, seg_len);
+    chain_plan(B, L, nblk, GFE_CBWD_MINB * (64 / cpc), nseg, seg_len);
 }
 
 // The chained kernels serve every shape with ED % 16 == 0 that offers enough (row, channel) parallelism to fill the GPU

@@ -266,6 +266,12 @@ static int persistent_grid(int nt, size_t smem, int total) {
 #ifndef GFE_BWD_CPC_DEFAULT
 #define GFE_BWD_CPC_DEFAULT 64
 #endif
+#ifndef GFE_CBWD_KEEP_A
+#define GFE_CBWD_KEEP_A 1      // backward: 1 = the decay factors of a half chunk stay in registers (64 more) instead of being re-derived
+#endif
+#ifndef GFE_CBWD_MINB
+#define GFE_CBWD_MINB 2        // backward: CTAs of 128 threads per SM the register budget is set for (2: 255 registers, 3: 168)
+#endif
 bool chain_applicable(int B, int L, int ED);              // shape-only: both directions take the same decision
 size_t chain_ckpt_state_bytes(int B, int L, int ED);
 size_t chain_fwd_workspace_bytes(int B, int L, int ED);

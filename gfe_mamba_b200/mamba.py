@@ -71,7 +71,14 @@ class Mamba(nn.Module):
 
     def forward(self, x):
         # x : (B, L, D) -> (B, L, D)
-        if not (x.is_cuda and _fusable_norm(x, self.config)):
+        if not x.is_cuda:
+            raise RuntimeError("gfe_mamba_b200.Mamba: CUDA tensors required (this library has no CPU fallback); "
+                               f"got input on {x.device}")
+        if len(self.layers) == 0:
+            return x
+        if not _fusable_norm(x, self.config):
+            # d_model outside the fused add + RMSNorm kernel's register-resident row (not a multiple of the 16-byte
+            # vector, or wider than 256 vectors): the reference's module-by-module form, same CUDA kernels in the mixer
             for layer in self.layers:
                 x = layer(x)
             return x
@@ -159,7 +166,10 @@ class MambaBlock(nn.Module):
         # x : (B, L, D) -> (B, L, D)          mamba.py:197-225
         xz = self.in_proj(x)                                  # (B, L, 2*ED)   GEMM
         xin, z = xz.chunk(2, dim=-1)                          # strided halves, consumed in place by the kernels
-        u = ops.causal_conv1d_silu(xin, self.conv1d.weight, self.conv1d.bias)   # conv + bias + SiLU fused (:208-212)
+        if 2 <= self.config.d_conv <= 4:
+            u = ops.causal_conv1d_silu(xin, self.conv1d.weight, self.conv1d.bias)   # conv + bias + SiLU fused (:208-212)
+        else:   # filter lengths the conv kernel is not compiled for (jamba.py passes arbitrary mamba_d_conv): cuDNN
+            u = F.silu(self.conv1d(xin.transpose(1, 2))[:, :, :x.shape[1]].transpose(1, 2))
         y = self._ssm_fused(u, z)                             # scan + D skip + SiLU(z) gate fused (:213-222)
         return self.out_proj(y)                               # GEMM
 
@@ -209,10 +219,22 @@ class MambaBlock(nn.Module):
         h, inputs = cache
         xz = self.in_proj(x)                                  # (B, 2*ED)
         xin, z = xz.chunk(2, dim=1)
-        u, inputs = ops.conv1d_step(xin, inputs, self.conv1d.weight, self.conv1d.bias)
+        if self._step_kernels_usable(xin, inputs, h) and 2 <= self.config.d_conv <= 4:
+            u, inputs = ops.conv1d_step(xin, inputs, self.conv1d.weight, self.conv1d.bias)
+        else:   # the reference's own window form (:357-358, 370): differentiable, any d_conv
+            x_cache = xin.unsqueeze(2)
+            u = F.silu(self.conv1d(torch.cat([inputs, x_cache], dim=2))[:, :, self.config.d_conv - 1])
+            inputs = torch.cat([inputs[:, :, 1:], x_cache], dim=2)
         y, h = self.ssm_step(u, h, z=z)
         output = self.out_proj(y)
         return output, (h, inputs)
+
+    def _step_kernels_usable(self, *tensors):
+        """The decode kernels are inference-only: a caller that backpropagates through ``step`` (the reference's step is
+        ordinary differentiable torch code) gets the torch composition instead of a silently detached graph."""
+        if not torch.is_grad_enabled():
+            return True
+        return not (any(t is not None and t.requires_grad for t in tensors) or any(p.requires_grad for p in self.parameters()))
 
     def ssm_step(self, x, h, z=None):
         """mamba.py:375-405 (+ the gate of :364-367 when ``z`` is given).  Returns (y, h_new)."""
@@ -220,7 +242,18 @@ class MambaBlock(nn.Module):
         delta, B, C = torch.split(deltaBC, [self.config.dt_rank, self.config.d_state, self.config.d_state], dim=-1)
         delta, B, C = self._apply_layernorms(delta, B, C)
         delta = F.linear(delta, self.dt_proj.weight)
-        return ops.ssm_step(x, delta, self.A_log, B, C, self.D, h, z=z, dt_bias=self.dt_proj.bias, delta_softplus=True)
+        if self.config.d_state == 16 and self._step_kernels_usable(x, h, z):
+            return ops.ssm_step(x, delta, self.A_log, B, C, self.D, h, z=z, dt_bias=self.dt_proj.bias, delta_softplus=True)
+        # other state sizes, or a caller that differentiates through the step: the reference's composition (:391-403)
+        A = -torch.exp(self.A_log.float())
+        delta = F.softplus(delta + self.dt_proj.bias)
+        deltaA = torch.exp(delta.unsqueeze(-1) * A)
+        BX = (delta.unsqueeze(-1) * B.unsqueeze(1)) * x.unsqueeze(-1)
+        if h is None:
+            h = torch.zeros(x.size(0), self.config.d_inner, self.config.d_state, device=deltaA.device)
+        h = deltaA * h + BX
+        y = (h @ C.unsqueeze(-1)).squeeze(2) + self.D.float() * x
+        return (y if z is None else y * F.silu(z)), h
 
 
 class RMSNorm(nn.Module):

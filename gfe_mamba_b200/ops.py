@@ -50,13 +50,14 @@ def _rows(t: torch.Tensor) -> torch.Tensor:
 _SIZE_CACHE = {}
 
 
-def _sizes(B: int, L: int, ED: int, N: int):
-    """(ckpt, fwd workspace, bwd workspace) bytes of one shape; pure functions of the shape, so asked once."""
-    key = (B, L, ED, N)
+def _sizes(B: int, L: int, ED: int, N: int, dev: torch.device, dtype: int):
+    """(ckpt, fwd workspace, bwd workspace) bytes of one shape ON ONE DEVICE (the launch plan depends on the device's
+    SM count, so the key carries the device); asked once.  Call with ``dev`` current."""
+    key = (B, L, ED, N, dev.index, dtype)
     v = _SIZE_CACHE.get(key)
     if v is None:
         l = nat.lib()
-        v = (l.gfe_selscan_ckpt_bytes(B, L, ED, N), l.gfe_selscan_fwd_workspace_bytes(B, L, ED, N),
+        v = (l.gfe_selscan_ckpt_bytes_dt(B, L, ED, N, dtype), l.gfe_selscan_fwd_workspace_bytes(B, L, ED, N),
              l.gfe_selscan_bwd_workspace_bytes(B, L, ED, N))
         _SIZE_CACHE[key] = v
     return v
@@ -143,7 +144,7 @@ class _SelectiveScanFn(torch.autograd.Function):
     (cross_atten/mamba.py:255-256, 265-286, 220-222; the contract of the selective_scan_fn call at mamba.py:251)."""
 
     @staticmethod
-    def forward(ctx, u, delta, A_log, Bm, Cm, D, z, dt_bias, softplus: bool, return_last_state: bool):
+    def forward(ctx, u, delta, A_log, Bm, Cm, D, z, dt_bias, softplus: bool, return_last_state: bool, grad_mode: bool):
         dev = _require_cuda(u, delta, A_log, Bm, Cm, D, z, dt_bias)
         if u.dim() != 3:
             raise ValueError(f"selective_scan: u must be (B, L, ED); got {tuple(u.shape)}")
@@ -160,14 +161,16 @@ class _SelectiveScanFn(torch.autograd.Function):
         A_log_, D_, bias_ = _f32(A_log), _f32(D), _f32(dt_bias)
         out = torch.empty((B, L, ED), dtype=dt, device=dev)
         last = torch.empty((B, ED, N), dtype=torch.float32, device=dev) if return_last_state else None
-        need_grad = any(ctx.needs_input_grad)
+        # needs_input_grad mirrors requires_grad and ignores the grad mode: under no_grad / eval with trainable parameters
+        # nothing is checkpointed (the checkpoint stream is larger than the forward's own traffic)
+        need_grad = grad_mode and any(ctx.needs_input_grad)
         l = nat.lib()
         a = nat.SelscanArgs()
         _fill_common(a, u_, delta_, z_, Bm_, Cm_, A_log_, D_, bias_, softplus)
         a.out, a.out_bs, a.out_rs = out.data_ptr(), out.stride(0), out.stride(1)
         a.last_state = 0 if last is None else last.data_ptr()
         with torch.cuda.device(dev):
-            sz = _sizes(B, L, ED, N)
+            sz = _sizes(B, L, ED, N, dev, _DT[dt])
             nck = sz[0] if need_grad else 0
             ckpt = _bytes(nck, dev)
             nws = sz[1]
@@ -214,7 +217,7 @@ class _SelectiveScanFn(torch.autograd.Function):
         a.dA_log, a.dD = dA_log.data_ptr(), dD.data_ptr()
         a.ddt_bias = 0 if dbias is None else dbias.data_ptr()
         with torch.cuda.device(dev):
-            nws = _sizes(B, L, ED, N)[2]
+            nws = _sizes(B, L, ED, N, dev, _DT[dt])[2]
             ws = _bytes(nws, dev)
             a.ws, a.ws_bytes = (0 if ws is None else ws.data_ptr()), nws
             nat.check(l.gfe_selscan_bwd(ctypes.byref(a), _stream(dev)), "selscan_bwd")
@@ -224,7 +227,7 @@ class _SelectiveScanFn(torch.autograd.Function):
             return None if (g is None or dts[i] is None) else (g if g.dtype == dts[i] else g.to(dts[i]))
 
         return (cast(du, 0), cast(ddelta, 1), cast(dA_log, 2), cast(dBm, 3), cast(dCm, 4), cast(dD, 5),
-                cast(dz, 6), cast(dbias, 7), None, None)
+                cast(dz, 6), cast(dbias, 7), None, None, None)
 
 
 def selective_scan_fn(u: torch.Tensor, delta: torch.Tensor, A_log: torch.Tensor, Bm: torch.Tensor, Cm: torch.Tensor,
@@ -237,7 +240,8 @@ def selective_scan_fn(u: torch.Tensor, delta: torch.Tensor, A_log: torch.Tensor,
         delta' = softplus(delta + dt_bias);  h_t = exp(delta' A) h_{t-1} + delta' B_t u_t,  A = -exp(A_log)
         out_t  = (C_t . h_t + D u_t) * silu(z_t)
     """
-    return _SelectiveScanFn.apply(u, delta, A_log, Bm, Cm, D, z, dt_bias, bool(delta_softplus), bool(return_last_state))
+    return _SelectiveScanFn.apply(u, delta, A_log, Bm, Cm, D, z, dt_bias, bool(delta_softplus), bool(return_last_state),
+                                  torch.is_grad_enabled())
 
 
 # ----------------------------------------------------------------------- causal conv1d + SiLU
@@ -297,7 +301,7 @@ class _AddRMSNormFn(torch.autograd.Function):
     (cross_atten/mamba.py:103) fused with the next RMSNorm (mamba.py:408-418).  SURVEY 8f rank 1."""
 
     @staticmethod
-    def forward(ctx, x, a, weight, eps: float):
+    def forward(ctx, x, a, weight, eps: float, grad_mode: bool):
         dev = _require_cuda(x, a, weight)
         if x.dtype not in _DT:
             raise TypeError(f"add_rmsnorm: unsupported activation dtype {x.dtype}")
@@ -310,7 +314,7 @@ class _AddRMSNormFn(torch.autograd.Function):
         rows = x_.numel() // D
         resid = torch.empty_like(x_) if a_ is not None else x_
         y = torch.empty_like(x_)
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = grad_mode and any(ctx.needs_input_grad)
         rstd = torch.empty(rows, dtype=torch.float32, device=dev) if need_grad else None
         l = nat.lib()
         with torch.cuda.device(dev):
@@ -338,22 +342,31 @@ class _AddRMSNormFn(torch.autograd.Function):
             ws = _bytes(nws, dev)
             nat.check(l.gfe_add_rmsnorm_bwd(_ptr(resid), _ptr(w_), _ptr(rstd), _ptr(dy_), _ptr(dres_), _ptr(dx), _ptr(dw), rows, D,
                                             _DT[resid.dtype], _ptr(ws), nws, _stream(dev)), "add_rmsnorm_bwd")
-        return dx, (dx if ctx.has_a else None), dw.to(ctx.wdtype), None
+        return dx, (dx if ctx.has_a else None), dw.to(ctx.wdtype), None, None
 
 
 def add_rmsnorm(x: torch.Tensor, a: Optional[torch.Tensor], weight: torch.Tensor, eps: float = 1e-5
                 ) -> Tuple[torch.Tensor, torch.Tensor]:
     """Returns (resid, y): resid = x + a (or x itself when a is None), y = RMSNorm(resid) * weight.  x, a: (..., D)."""
-    return _AddRMSNormFn.apply(x, a, weight, eps)
+    return _AddRMSNormFn.apply(x, a, weight, eps, torch.is_grad_enabled())
 
 
 # ------------------------------------------------------------------------------- decode step
-@torch.no_grad()
+def _no_autograd(name: str, *ts):
+    """The decode kernels have no backward: refuse to silently detach a graph (MambaBlock.step falls back to the
+    reference's differentiable torch composition in that case)."""
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts):
+        raise RuntimeError(f"gfe_mamba_b200.{name}: inputs require grad but the decode kernels are inference-only; "
+                           "call under torch.no_grad() or use MambaBlock.step, which falls back to torch ops")
+
+
 def conv1d_step(xin: torch.Tensor, inputs: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]
                 ) -> Tuple[torch.Tensor, torch.Tensor]:
     """One token of the causal conv (mamba.py:357-358, 370).  xin: (B, ED); inputs: (B, ED, K-1).
     Returns (u, new_inputs); ``inputs`` is not modified."""
     dev = _require_cuda(xin, inputs, weight, bias)
+    _no_autograd("conv1d_step", xin, inputs, weight, bias)
+    xin, inputs, weight = xin.detach(), inputs.detach(), weight.detach()
     B, ED = xin.shape
     K = weight.shape[-1]
     dt = xin.dtype
@@ -369,19 +382,20 @@ def conv1d_step(xin: torch.Tensor, inputs: torch.Tensor, weight: torch.Tensor, b
     return u, new_inputs
 
 
-@torch.no_grad()
 def ssm_step(u, delta, A_log, Bm, Cm, D, h, z=None, dt_bias=None, delta_softplus: bool = True):
     """One token of the selective scan (mamba.py:375-405).  u, delta, z: (B, ED); Bm, Cm: (B, N); h: (B, ED, N) or None.
     Returns (out, h_new); ``h`` is not modified."""
     dev = _require_cuda(u, delta, A_log, Bm, Cm, D, h, z, dt_bias)
+    _no_autograd("ssm_step", u, delta, A_log, Bm, Cm, D, h, z, dt_bias)
     B, ED = u.shape
     N = A_log.shape[1]
     dt = u.dtype
+    h = None if h is None else h.detach()
 
     def row(t):
         if t is None:
             return None
-        t = t.to(dt)
+        t = t.detach().to(dt)
         return t if t.stride(-1) == 1 else t.contiguous()
 
     u_, delta_, z_, Bm_, Cm_ = row(u), row(delta), row(z), row(Bm), row(Cm)

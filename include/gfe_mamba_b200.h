@@ -111,7 +111,8 @@ typedef struct gfe_selscan_args {
     float *ddt_bias;                               /* (ED) or NULL, overwritten */
 } gfe_selscan_args;
 
-GFE_API size_t gfe_selscan_ckpt_bytes(int B, int L, int ED, int N);
+GFE_API size_t gfe_selscan_ckpt_bytes(int B, int L, int ED, int N);            /* upper bound over the dtypes (fp32) */
+GFE_API size_t gfe_selscan_ckpt_bytes_dt(int B, int L, int ED, int N, int dtype); /* exact, for one gfe_dtype          */
 GFE_API size_t gfe_selscan_fwd_workspace_bytes(int B, int L, int ED, int N);
 GFE_API size_t gfe_selscan_bwd_workspace_bytes(int B, int L, int ED, int N);
 GFE_API int gfe_selscan_fwd(const gfe_selscan_args *args, void *stream);
@@ -157,6 +158,25 @@ GFE_API size_t gfe_add_rmsnorm_bwd_workspace_bytes(int64_t rows, int D);
 GFE_API int gfe_add_rmsnorm_bwd(const void *resid, const float *w, const float *rstd, const void *dy, const void *dres,
                                 void *dx, float *dw, int64_t rows, int D, int dtype, void *ws, size_t ws_bytes,
                                 void *stream);
+
+/* ------------------------------------------- multi-tensor clip + Adam step --
+ * One optimiser step for a whole parameter list in three launches; replaces the per-parameter loop
+ *     for p in params: torch.nn.utils.clip_grad_norm_(p, max_norm)      (classify_mamba.py:106-107)
+ *     optimizer.step(); optimizer.zero_grad()                            (classify_mamba.py:108-109, torch.optim.Adam)
+ * All tables live in DEVICE memory and are built once by the caller:
+ *   p_ptr, g_ptr, m_ptr, v_ptr [ntensors]  device addresses (as int64) of the fp32 parameter, gradient, exp_avg, exp_avg_sq
+ *   numel [ntensors];  the tensors are cut into chunks of gfe_clip_adam_chunk_elems() elements:
+ *   chunk_tensor [nchunks], chunk_start [nchunks] (element offset in the tensor), tensor_chunk0 [ntensors + 1]
+ *   partial [nchunks], coef [ntensors]  scratch;  step [1]  int32 step counter, incremented by the call
+ * clip: coef = min(1, max_norm / (norm + 1e-6)) per tensor (global_norm = 0, the reference loop) or over the whole
+ * list (global_norm = 1); max_norm <= 0 disables clipping.  zero_grad != 0 leaves the gradients zeroed, else clipped.
+ */
+GFE_API int gfe_clip_adam_chunk_elems(void);
+GFE_API int gfe_clip_adam_step(const int64_t *p_ptr, const int64_t *g_ptr, const int64_t *m_ptr, const int64_t *v_ptr,
+                               const int64_t *numel, const int32_t *chunk_tensor, const int64_t *chunk_start,
+                               const int32_t *tensor_chunk0, float *partial, float *coef, int32_t *step, int ntensors,
+                               int nchunks, float lr, float beta1, float beta2, float eps, float max_norm, int global_norm,
+                               int zero_grad, void *stream);
 
 /* -------------------------------------------------------- instrumentation --
  * Optional per-kernel device timing: when enabled, every kernel the library launches is bracketed by a

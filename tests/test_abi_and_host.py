@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
     lib = _native.lib()                      # also checks every signature in the ctypes table resolves
     assert set(_native.SIGNATURES) == set(_declared_symbols())
     assert lib.gfe_version() == 100
-    assert lib.gfe_timing_kernel_count() == 18 and lib.gfe_timing_kernel_name(3) == b"selscan_bwd"
+    assert lib.gfe_timing_kernel_count() == 21 and lib.gfe_timing_kernel_name(3) == b"selscan_bwd"
 
 
 def test_size_queries_without_gpu():
@@ -46,6 +46,9 @@ def test_size_queries_without_gpu():
     assert lib.gfe_selscan_ckpt_bytes(B, L, ED, N) == states + B * L * ED * 4
     assert lib.gfe_selscan_ckpt_bytes(1, 65536, 1024, N) == (65536 // 16) * 1024 * N * 4 + 65536 * 1024 * 4   # L-split path: 16
     assert lib.gfe_selscan_ckpt_bytes(B, L, ED, 8) == 0            # unsupported d_state -> 0
+    # y before the gate is kept in the activation dtype: bf16 halves that part
+    assert lib.gfe_selscan_ckpt_bytes_dt(B, L, ED, N, _native.GFE_BF16) == states + B * L * ED * 2
+    assert lib.gfe_selscan_ckpt_bytes_dt(B, L, ED, N, _native.GFE_F32) == lib.gfe_selscan_ckpt_bytes(B, L, ED, N)
     # one dB|dC row (32 fp32) per (channel block of <= 64 channels, token)
     assert (ED // 64) * B * L * 32 * 4 <= lib.gfe_selscan_bwd_workspace_bytes(B, L, ED, N) < (ED // 32) * B * L * 32 * 4
     # chained segments: counter + flags + one (B, ED, N) fp32 carry; far below one activation tensor
