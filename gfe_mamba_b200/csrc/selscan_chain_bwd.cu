@@ -46,7 +46,9 @@ struct BwdChainSmem {
     static constexpr int kTile = kChunk * CPC * (int)sizeof(T);         // one of u, delta, dout, y, z
     static constexpr int kNTile = HAS_Z ? 5 : 3;
     static constexpr int kBCRaw = kChunk * kNState * (int)sizeof(T);     // one of B, C
-    static constexpr int kStage = kNTile * kTile + 2 * kBCRaw;
+    static constexpr int kCk = CPC * kNState * 4;                        // the checkpoints of one half chunk: [c][16] fp32
+    static constexpr int kOffCk = kNTile * kTile + 2 * kBCRaw;           // inside a stage: both halves' checkpoints
+    static constexpr int kStage = kOffCk + 2 * kCk;
     static constexpr int kSPlane = NP + 2;                               // float4 per (t, quad) plane of the partials (+32 B skew)
     static constexpr int kOffDD = kStages * kStage;                      // float4 [16][NP] {dl0, dl0 u0, dl1, dl1 u1}
     static constexpr int kOffDY = kOffDD + kChunk * NP * 16;             // float2 [16][NP] {dy0, dy1}
@@ -68,6 +70,7 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
     constexpr int BCP = kChunk * kNState * (int)sizeof(T) / 16;   // pieces per B (or C) tile: 32 (16-bit), 64 (fp32)
     constexpr int BCI = (2 * BCP + NT - 1) / NT;      // B|C pieces per thread
     constexpr int BCC = kChunk * 8 / NT;              // fp32 B|C quads converted per thread
+    constexpr int CKP = 2 * SM::kCk / 16 / NT;        // 16-byte checkpoint pieces per thread and chunk (4)
     constexpr int SPL = SM::kSPlane;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rp = tid >> 2, rq = tid & 3;     // recurrence mapping: channel pair in block, state quad
@@ -119,10 +122,10 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
         const T *zb = HAS_Z ? reinterpret_cast<const T *>(p.z) + (int64_t)b * p.z_bs + c0 : nullptr;
         const T *Bb = reinterpret_cast<const T *>(p.Bm) + (int64_t)b * p.B_bs;
         const T *Cb = reinterpret_cast<const T *>(p.Cm) + (int64_t)b * p.C_bs;
-        // this lane's checkpointed quads: [b][t / 8][c][16] fp32, channels 2 rp and 2 rp + 1
-        const float4 *ckq = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(p.ckpt) +
-                                                             ((size_t)b * p.nchunks * p.ED + c0 + 2 * rp) * kNState) + rq;
-        const size_t ck_step = (size_t)p.ED * (kNState / 4);   // float4 between consecutive checkpoints
+        // checkpoints [b][t / 8][c][16] fp32: the block's CPC channels of one half chunk are contiguous (staged with the tiles)
+        const char *ckb = reinterpret_cast<const char *>(reinterpret_cast<const float *>(p.ckpt) +
+                                                         ((size_t)b * p.nchunks * p.ED + c0) * kNState);
+        const size_t ck_step = (size_t)p.ED * kNState * sizeof(float);   // bytes between consecutive checkpoints
         T *dub = reinterpret_cast<T *>(p.du) + (int64_t)b * p.du_bs + c0 + 2 * cp;
         T *ddb = reinterpret_cast<T *>(p.ddelta) + (int64_t)b * p.dd_bs + c0 + 2 * cp;
         T *dzb = HAS_Z ? reinterpret_cast<T *>(p.dz) + (int64_t)b * p.dz_bs + c0 + 2 * ip : nullptr;
@@ -151,11 +154,22 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
         const uint32_t dst_act = smem_u32(smem) + srow * RB + spiece * 16;
         const uint32_t dst_bc = smem_u32(smem) + NTILE * SM::kTile + tid * 16;   // raw B tile followed by raw C tile
 
-        auto issue = [&](int i) {   // i-th chunk in processing order (global chunk klast - i) -> stage i % NST
+        auto issue = [&](int i, int stage) {   // i-th chunk in processing order (global chunk klast - i) -> stage i % NST
             if (i < nch) {
                 const int tb = (klast - i) * kChunk;
                 const int nrows = min(kChunk, t1 - tb);
-                const uint32_t so = (i % NST) * SM::kStage;
+                const uint32_t so = stage * SM::kStage;
+                {   // both halves' checkpoints (states before steps tb and tb + 8); always 16-byte aligned
+                    const int nhalf = tb + kCkptV2 < t1 ? 2 : 1;
+#pragma unroll
+                    for (int q = 0; q < CKP; ++q) {
+                        const int pc = tid + q * NT;                        // piece of [half][c][16]
+                        const int half = pc / (SM::kCk / 16), within = pc % (SM::kCk / 16);
+                        if (half < nhalf)
+                            cp_async<16>(smem_u32(smem) + so + SM::kOffCk + pc * 16,
+                                         ckb + (size_t)(2 * (klast - i) + half) * ck_step + within * 16);
+                    }
+                }
                 if constexpr (CPB == 16) {
                     if (srow < nrows) {
                         const int64_t sz_t = (int64_t)sizeof(T);
@@ -190,7 +204,7 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
             cp_async_commit();
         };
 #pragma unroll
-        for (int i = 0; i < NST; ++i) issue(i);
+        for (int i = 0; i < NST; ++i) issue(i, i);
 
         // per-thread constants (state pairs swapped when sw)
         float2 A2[2][2], G[2][2], dA[2][2];
@@ -224,9 +238,9 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
             for (int ch = 0; ch < 2; ++ch) G[ch][0] = G[ch][1] = make_float2(0.f, 0.f);
         }
 
-        auto phase_a = [&](int i) {
+        auto phase_a = [&](int i, int stage) {
             const int tb = (klast - i) * kChunk;
-            const unsigned char *s = smem + (i % NST) * SM::kStage;
+            const unsigned char *s = smem + stage * SM::kStage;
             const T *sU = reinterpret_cast<const T *>(s);
             const T *sD = reinterpret_cast<const T *>(s + SM::kTile);
             const T *sDo = reinterpret_cast<const T *>(s + 2 * SM::kTile);
@@ -239,7 +253,7 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
                 const float2 d2 = lds_pair(sD + (ir + 4 * q) * CPC, ip);
                 const float2 x = make_float2(d2.x + bias.x, d2.y + bias.y);
                 float2 sg2;
-                const float2 v = softplus2<true>(x, sg2);
+                const float2 v = softplus_pair<true>(x, sg2);
                 dl[q] = sp ? v : x;
                 sg[q] = sp ? sg2 : make_float2(1.0f, 1.0f);
             }
@@ -297,16 +311,9 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
 
         cp_async_wait<NST - 1>();
         __syncthreads();
-        phase_a(0);
-        // checkpoints of the first chunk (states before its steps 0 and 8), both channels
-        float4 ck_lo[2], ck_hi[2];
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-            ck_lo[ch] = __ldcs(ckq + (size_t)(2 * klast) * ck_step + ch * (kNState / 4));
-            ck_hi[ch] = (klast * kChunk + kCkptV2 < t1) ? __ldcs(ckq + (size_t)(2 * klast + 1) * ck_step + ch * (kNState / 4))
-                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        phase_a(0, 0);
 
+        int stage = 0;   // i % NST
         for (int i = 0; i < nch; ++i) {
             const int k = klast - i;
             const int tb = k * kChunk;
@@ -327,7 +334,8 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
 #endif
 #pragma unroll
                 for (int ch = 0; ch < 2; ++ch) {
-                    const float4 ck = half ? ck_hi[ch] : ck_lo[ch];
+                    const float4 ck = *(reinterpret_cast<const float4 *>(smem + stage * SM::kStage + SM::kOffCk + half * SM::kCk) +
+                                        (2 * rp + ch) * (kNState / 4) + rq);
                     h0[ch][0] = sw ? make_float2(ck.y, ck.x) : make_float2(ck.x, ck.y);
                     h1[ch][0] = sw ? make_float2(ck.w, ck.z) : make_float2(ck.z, ck.w);
                 }
@@ -446,14 +454,8 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
 
             cp_async_wait<NST - 2>();
             __syncthreads();   // (2) per-warp dB|dC rows complete; next chunk visible; this chunk's stage free
-            issue(i + NST);
-            if (i + 1 < nch) {   // next chunk's checkpoints travel while the row sums and phase A run
-#pragma unroll
-                for (int ch = 0; ch < 2; ++ch) {
-                    ck_lo[ch] = __ldcs(ckq + (size_t)(2 * (k - 1)) * ck_step + ch * (kNState / 4));
-                    ck_hi[ch] = __ldcs(ckq + (size_t)(2 * (k - 1) + 1) * ck_step + ch * (kNState / 4));
-                }
-            }
+            issue(i + NST, stage);
+            stage = stage + 1 == NST ? 0 : stage + 1;
             // dB|dC rows of this CTA: add the warps' tiles; row layout {dB[n], dC[n]} interleaved
 #pragma unroll
             for (int q = 0; q < BCC; ++q) {
@@ -470,7 +472,7 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
                     __stcs(reinterpret_cast<float4 *>(p.part_bc + (((size_t)blk * p.B + b) * p.L + tb + t) * 32) + q8, acc);
                 }
             }
-            if (i + 1 < nch) phase_a(i + 1);
+            if (i + 1 < nch) phase_a(i + 1, stage);
         }
 
         // ---- end of unit: parameter-gradient partials, carry-out ----

@@ -13,10 +13,15 @@ namespace gfe {
 template <typename T>
 void v4_launch_fwd_kernel(const ScanParams &p, const ChainSched &cs, int cpc, bool has_z, int cpb, cudaStream_t st);   // selscan_v4_fwd.cu
 
-// Units per launch are sized for ~8 per resident CTA.
+// L is cut into chained segments, ~12 units per resident CTA: the units of a chain interleave with those of the others and
+// hop between SMs, which evens out SMs that host 2 and 3 working CTAs (measured on cfg3, profiles/r02_chain_variants.txt:
+// 10-16 segments beat 1, 4 and 32 by 2-4 %).
 static void chain_plan(int B, int L, int nblk, int ctas_per_sm, int &nseg, int &seg_len) {
     const int64_t slots = (int64_t)sm_count() * ctas_per_sm;
-    int64_t want = ceil_div64(8 * slots, (int64_t)B * nblk);
+    int64_t want = ceil_div64(12 * slots, (int64_t)B * nblk);
+#ifdef GFE_EXPERIMENTS
+    if (const char *e = getenv("GFE_CHAIN_NSEG")) want = atoi(e);   // A/B measurements only
+#endif
     const int64_t max_by_len = L / (8 * kChunk) > 0 ? L / (8 * kChunk) : 1;   // >= 128 steps per segment
     if (want > max_by_len) want = max_by_len;
     if (want > kMaxSeg) want = kMaxSeg;

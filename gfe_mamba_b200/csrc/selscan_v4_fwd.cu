@@ -173,11 +173,11 @@ __global__ void __launch_bounds__(2 * CPC, GFE_V4_MINB * (64 / CPC)) selscan_fwd
         const uint32_t dst_act = smem_u32(smem) + srow * RB + spiece * 16;
         const uint32_t dst_bc = smem_u32(smem) + NTILE * SM::kTile + tid * 16;   // the raw B tile is followed by the raw C tile
 
-        auto issue = [&](int k) {   // chunk k of this segment -> stage k % NST
+        auto issue = [&](int k, int stage) {   // chunk k of this segment -> stage k % NST
             if (k < nch) {
                 const int tb = t0 + k * kChunk;
                 const int nrows = min(kChunk, t1 - tb);
-                const uint32_t so = (k % NST) * SM::kStage;
+                const uint32_t so = stage * SM::kStage;
                 if constexpr (CPB == 16) {
                     if (srow < nrows) {
 #pragma unroll
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(2 * CPC, GFE_V4_MINB * (64 / CPC)) selscan_fwd
             cp_async_commit();
         };
 #pragma unroll
-        for (int k = 0; k < NST; ++k) issue(k);
+        for (int k = 0; k < NST; ++k) issue(k, k);
 
         // per-thread constants: A of both channels (recurrence mapping), D and bias (item mapping)
         float2 A2[2][2], h[2][2];
@@ -235,37 +235,22 @@ __global__ void __launch_bounds__(2 * CPC, GFE_V4_MINB * (64 / CPC)) selscan_fwd
         }
 
         float2 Du[4], gate[4];
-        auto phase_a = [&](int k) {   // per-(t, channel pair) scalars of chunk k -> shared slots; B|C rows -> fp32 quads
+        auto phase_a = [&](int k, int stage) {   // per-(t, channel pair) scalars of chunk k -> shared slots; B|C rows -> fp32 quads
             const int tb = t0 + k * kChunk;
-            const unsigned char *s = smem + (k % NST) * SM::kStage;
+            const unsigned char *s = smem + stage * SM::kStage;
             const T *sU = reinterpret_cast<const T *>(s);
             const T *sD = reinterpret_cast<const T *>(s + SM::kTile);
             const T *sZ = reinterpret_cast<const T *>(s + 2 * SM::kTile);
             const T *sBr = reinterpret_cast<const T *>(s + NTILE * SM::kTile);   // B rows then C rows
-            float x[8], dl[8], sg[8];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 d2 = lds_pair(sD + (ir + 4 * i) * CPC, ip);
-                x[2 * i] = d2.x + bias.x;
-                x[2 * i + 1] = d2.y + bias.y;
-            }
-#if GFE_SOFTPLUS2
+            float2 dl[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {   // branch-free packed softplus (selscan_shared.cuh)
+                const float2 d2 = lds_pair(sD + (ir + 4 * i) * CPC, ip);
+                const float2 x = fadd2(d2, bias);
                 float2 sg2;
-                const float2 v = softplus2<false>(make_float2(x[2 * i], x[2 * i + 1]), sg2);
-                dl[2 * i] = sp ? v.x : x[2 * i];
-                dl[2 * i + 1] = sp ? v.y : x[2 * i + 1];
+                const float2 v = softplus_pair<false>(x, sg2);
+                dl[i] = sp ? v : x;
             }
-            (void)sg;
-#else
-            if (sp) {
-                softplus_group<8, false>(x, dl, sg);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) dl[i] = x[i];
-            }
-#endif
             float2 uq[4], zq[4];   // every load of the phase before its first store (an LDS is never moved above an STS)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -290,7 +275,7 @@ __global__ void __launch_bounds__(2 * CPC, GFE_V4_MINB * (64 / CPC)) selscan_fwd
                 const bool valid = tb + t < t1;
                 const float2 u2 = uq[i];
                 const float u0 = valid ? u2.x : 0.f, u1 = valid ? u2.y : 0.f;
-                const float dl0 = valid ? dl[2 * i] : 0.f, dl1 = valid ? dl[2 * i + 1] : 0.f;   // padded step: a = 1, bx = 0
+                const float dl0 = valid ? dl[i].x : 0.f, dl1 = valid ? dl[i].y : 0.f;   // padded step: a = 1, bx = 0
                 sDD[t * NP + ip] = make_float4(dl0, dl0 * u0, dl1, dl1 * u1);
                 Du[i] = make_float2(Dc.x * u0, Dc.y * u1);
                 if (HAS_Z) {
@@ -304,15 +289,21 @@ __global__ void __launch_bounds__(2 * CPC, GFE_V4_MINB * (64 / CPC)) selscan_fwd
 
         cp_async_wait<NST - 1>();
         __syncthreads();
-        phase_a(0);
+        phase_a(0, 0);
+        // running output pointers of this thread's item rows (row ir of the current chunk)
+        T *op = ob + (int64_t)(t0 + ir) * p.o_rs;
+        T *yp_g = yb != nullptr ? yb + (int64_t)(t0 + ir) * p.ED : nullptr;
+        const int64_t o_step = 4 * p.o_rs, y_step = (int64_t)4 * p.ED;
 
+        int stage = 0;   // k % NST
         for (int k = 0; k < nch; ++k) {
             const int tb = t0 + k * kChunk;
             __syncthreads();   // (1) slots of chunk k are complete
             v4_recur_chunk<CPC>(dd_r, bc_r, y_w, A2, h, ckq, ck_step, tb, t1);   // 16 steps of this lane's 2 x 4 states
             cp_async_wait<NST - 2>();   // chunk k + 1 has landed (this thread's pieces)
             __syncthreads();            // (2) partial sums complete; chunk k + 1 visible; stage k % NST free
-            issue(k + NST);
+            issue(k + NST, stage);
+            stage = stage + 1 == NST ? 0 : stage + 1;
 
             // ---- per-(t, channel pair) epilogue of chunk k: sum the 4 quads, D skip, gate, store ----
 #pragma unroll
@@ -321,14 +312,15 @@ __global__ void __launch_bounds__(2 * CPC, GFE_V4_MINB * (64 / CPC)) selscan_fwd
                 if (tb + t < t1) {
                     const float2 *yp = sY + (t * 4) * kV4YPlane + ip;
                     const float2 p0 = yp[0], p1 = yp[kV4YPlane], p2 = yp[2 * kV4YPlane], p3 = yp[3 * kV4YPlane];
-                    float y0 = (p0.x + p1.x) + (p2.x + p3.x) + Du[i].x;
-                    float y1 = (p0.y + p1.y) + (p2.y + p3.y) + Du[i].y;
-                    if (yb != nullptr) stg_pair<T>(yb + (int64_t)(tb + t) * p.ED, y0, y1, true);
-                    if (HAS_Z) { y0 *= gate[i].x; y1 *= gate[i].y; }
-                    stg_pair<T>(ob + (int64_t)(tb + t) * p.o_rs, y0, y1, vec);
+                    float2 y2 = fadd2(fadd2(fadd2(p0, p1), fadd2(p2, p3)), Du[i]);
+                    if (yp_g != nullptr) stg_pair<T>(yp_g, y2.x, y2.y, true);
+                    if (HAS_Z) y2 = fmul2(y2, gate[i]);
+                    stg_pair<T>(op, y2.x, y2.y, vec);
                 }
+                op += o_step;
+                if (yp_g != nullptr) yp_g += y_step;
             }
-            if (k + 1 < nch) phase_a(k + 1);
+            if (k + 1 < nch) phase_a(k + 1, stage);
         }
 
         // carry-out / final state

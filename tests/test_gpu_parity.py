@@ -160,7 +160,9 @@ def test_selscan_half_precision(dtype):
 
 # ---- the chained kernels (selscan_v4_fwd / selscan_v2_{fwd,bwd}): selected when B * ED / 32 >= 296 warps -----------------
 @pytest.mark.parametrize("B,L,ED", [(24, 203, 512),    # ragged L (not a multiple of 8 / 16), one segment
-                                    (20, 1000, 512),   # several chained L-segments, ragged last one
+                                    (20, 1000, 512),   # every chain has a CTA of its own: one unit per chain, ragged tail
+                                    (40, 400, 1024),   # more chains (640) than resident CTAs: three chained L-segments
+                                    (10, 1170, 4096),  # same, 64-channel blocks on both sides, ragged last segment
                                     (24, 203, 480),    # ED % 64 == 32: v2 forward (32-channel blocks)
                                     (40, 16, 256), (40, 1, 256), (40, 9, 256)])   # shorter than one chunk
 def test_selscan_chained_fp32_vs_oracle(B, L, ED):
