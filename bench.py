@@ -56,15 +56,43 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+KERNEL_SOURCES = ("selscan_v4_fwd.cu", "selscan_chain_bwd.cu", "selscan_chain_host.cu", "selscan_shared.cuh", "selscan.cu",
+                  "selscan_fast.cuh", "common.cuh")
+
+
+def kernel_source_hash():
+    """Fingerprint of the scan-kernel sources; tools/ncu_traffic.py stores it with every capture so that a capture taken
+    from other kernels than the ones being benchmarked is recognised as stale instead of being quoted."""
+    import hashlib
+    h = hashlib.sha256()
+    for name in KERNEL_SOURCES:
+        try:
+            with open(os.path.join(ROOT, "gfe_mamba_b200", "csrc", name), "rb") as f:
+                h.update(f.read())
+        except OSError:
+            h.update(name.encode())
+    return h.hexdigest()[:16]
+
+
 def measured_traffic(workload, kernel, B):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed `ncu --set full` capture
-    of this workload (profiles/traffic.json, written by tools/ncu_traffic.py); None when no capture exists for it."""
+    """(bytes, note): dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed
+    `ncu --set full` capture of this workload (profiles/traffic.json, written by tools/ncu_traffic.py).  None when no capture
+    exists for it or when the capture was taken from different kernel sources (stale)."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             rec = json.load(f)[workload]
-        return int(rec["kernels"][kernel]) if rec.get("batch_per_gpu") == B else None
     except Exception:
-        return None
+        return None, "no ncu capture for this workload"
+    if rec.get("batch_per_gpu") != B:
+        return None, "capture is for another batch size"
+    if rec.get("source_hash") != kernel_source_hash():
+        print(f"bench.py: WARNING profiles/traffic.json[{workload}] was captured from other kernel sources "
+              f"({rec.get('source_hash')} != {kernel_source_hash()}): not quoted; re-run tools/gpu_check.sh", file=sys.stderr)
+        return None, "stale capture (kernel sources changed since); ignored"
+    try:
+        return int(rec["kernels"][kernel]), rec.get("source", "")
+    except Exception:
+        return None, "kernel not in the capture"
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -149,6 +177,64 @@ def cpu_reference(B, L, ED, steps, warmup, budget_s):
                       f"fwd+bwd, {steps} timed samples; tokens/s is flat in B and L (BASELINE.md section 2)"}
 
 
+# ------------------------------------------------------------------------- multi-GPU correctness, visible in the JSON line
+def sharded_parity_check(dist, dev, rank, world, by_channels):
+    """Before timing, every rank runs ITS shard of one small shared problem through the same code path the timed loop uses
+    (batch rows, or ED channels with the dB/dC all-reduce); the shards are gathered and rank 0 compares them with the whole
+    problem computed on one GPU.  Returns {"mode", "max_rel_err", "tol", "ok"} (max-normalised error over out and every
+    gradient); raises on failure so that a wrong multi-GPU number is never printed."""
+    import torch
+    from gfe_mamba_b200 import selective_scan_fn
+    from gfe_mamba_b200.parallel import channel_sharded_scan, shard_batch, shard_channels
+    Bp, Lp, EDp = 2 * world, 200, 64 * world
+    g = torch.Generator(device=dev).manual_seed(99)          # same seed on every rank: one shared problem
+    rn = lambda *s: torch.randn(*s, device=dev, generator=g)
+    full = dict(u=rn(Bp, Lp, EDp), delta=rn(Bp, Lp, EDp) * 0.5, z=rn(Bp, Lp, EDp), Bm=rn(Bp, Lp, N_STATE), Cm=rn(Bp, Lp, N_STATE),
+                dout=rn(Bp, Lp, EDp))
+    A_log = torch.log(torch.arange(1, N_STATE + 1, device=dev).float()).repeat(EDp, 1) + 0.1 * rn(EDp, N_STATE)
+    Dp = 1 + 0.1 * rn(EDp)
+    bias = rn(EDp) * 0.3 - 3.0
+
+    def run(u, delta, z, Bm, Cm, dout, A, D, b, sharded):
+        lv = [t.clone().requires_grad_() for t in (u, delta, z, Bm, Cm, A, D, b)]
+        if sharded and by_channels:
+            out = channel_sharded_scan(selective_scan_fn, lv[0], lv[1], lv[5], lv[3], lv[4], lv[6], z=lv[2], dt_bias=lv[7])
+        else:
+            out = selective_scan_fn(lv[0], lv[1], lv[5], lv[3], lv[4], lv[6], z=lv[2], dt_bias=lv[7])
+        grads = torch.autograd.grad(out, lv, dout)
+        return [out.detach()] + [x.detach() for x in grads]
+
+    if by_channels:
+        ch = lambda t: shard_channels(t, rank, world).contiguous()
+        mine = run(ch(full["u"]), ch(full["delta"]), ch(full["z"]), full["Bm"], full["Cm"], ch(full["dout"]),
+                   shard_channels(A_log, rank, world, dim=0).contiguous(), ch(Dp), ch(bias), True)
+        cat_dim = {0: 2, 1: 2, 2: 2, 3: 2, 4: None, 5: None, 6: 0, 7: 0, 8: 0}       # dB/dC are already all-reduced
+    else:
+        sb = lambda t: shard_batch(t, rank, world).contiguous()
+        mine = run(sb(full["u"]), sb(full["delta"]), sb(full["z"]), sb(full["Bm"]), sb(full["Cm"]), sb(full["dout"]), A_log, Dp, bias, True)
+        for t in mine[6:]:                                                           # parameter gradients: summed over ranks
+            dist.all_reduce(t)
+        cat_dim = {0: 0, 1: 0, 2: 0, 3: 0, 4: 0, 5: 0, 6: None, 7: None, 8: None}
+    gathered = []
+    for i, t in enumerate(mine):
+        if cat_dim[i] is None:
+            gathered.append(t)
+        else:
+            parts = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(parts, t.contiguous())
+            gathered.append(torch.cat(parts, dim=cat_dim[i]))
+    res = None
+    if rank == 0:
+        want = run(full["u"], full["delta"], full["z"], full["Bm"], full["Cm"], full["dout"], A_log, Dp, bias, False)
+        err = max(float((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-30)) for a, b in zip(gathered, want))
+        res = {"mode": "channels" if by_channels else "batch", "shape": [Bp, Lp, EDp], "max_rel_err": err, "tol": 1e-4, "ok": err < 1e-4}
+    flag = torch.tensor([1 if (res is None or res["ok"]) else 0], device=dev)
+    dist.broadcast(flag, 0)
+    if int(flag.item()) != 1:
+        raise SystemExit(f"bench.py: sharded result differs from the single-GPU result: {res}")
+    return res
+
+
 # ------------------------------------------------------------------------------------------------ main
 def _claim_stdout():
     """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner at init), so the
@@ -168,7 +254,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default=None, choices=[None, "f32", "bf16", "f16"])
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--e2e-rows", type=int, default=0, help="batch rows per pipeline chunk of the e2e leg (0 = B/4)")
     ap.add_argument("--batch", type=int, default=0, help="override the workload's per-GPU batch (A/B measurements)")
     ap.add_argument("--shard", default="batch", choices=["batch", "channels"],
@@ -201,9 +287,9 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        r = cpu_reference(B, L, ED, args.steps, min(warmup, 3), budget_s=150.0)
+        r = cpu_reference(B, L, ED, args.steps, warmup, budget_s=150.0)
         line = {"impl": "reference", "metric": "selective-scan fwd+bwd tokens/s", "value": r["tokens_per_s"], "unit": "tokens/s",
-                "n_gpus": args.gpus, "steps": args.steps, "warmup": min(warmup, 3), "ms_per_step": r["ms_per_step"],
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": warmup, "ms_per_step": r["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": cfg,
                 "cpu_baseline": {"value": r["tokens_per_s"], "unit": "tokens/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
@@ -264,6 +350,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    parity = sharded_parity_check(dist, dev, rank, world, by_channels) if world > 1 else None
+
     for i in range(warmup):
         step(i)
     sync_all()
@@ -317,12 +405,13 @@ def main():
     dom = kern_list[0]
     dom_alg = {"selscan_fwd": fwd_b, "selscan_bwd": bwd_b}.get(dom["kernel"], fwd_b + bwd_b)
     achieved = dom_alg / (dom["avg_ms"] * 1e-3) / 1e9
+    traffic, traffic_note = measured_traffic(args.workload, dom["kernel"], B)
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": measured_traffic(args.workload, dom["kernel"], B), "peak_source": peak_src,
+                "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_alg,
                 "step_achieved": round((fwd_b + bwd_b) / (ms_per_step * 1e-3) / 1e9, 1),
                 "step_frac": round((fwd_b + bwd_b) / (ms_per_step * 1e-3) / 1e9 / peak, 4),
-                "note": "selective scan at N=16 is MUFU/FP32-pipe co-limited on B200 (DESIGN.md, 'Why not 60 %')"}
+                "note": "selective scan at N=16 is bound by MUFU + FP32 operand delivery on B200, not by HBM (DESIGN.md section 4)"}
     gpu_launches = int(sum(v[1] for v in kern.values()))
 
     # ---- e2e: the same step through the public host-buffer API (gfe_mamba_b200.host_pipeline.HostScanPipeline): pinned HOST
@@ -375,6 +464,8 @@ def main():
                 "scaling": "strong" if by_channels else "weak", "vs_baseline": None, "dtype": dts, "data": "synthetic", "config": cfg,
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
                 "kernels": kern_list}
+        if parity is not None:
+            line["parity_check"] = parity
         print(json.dumps(line), file=out_stream, flush=True)
     if world > 1:
         dist.destroy_process_group()

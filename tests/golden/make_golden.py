@@ -13,6 +13,8 @@ with the CUDA path directly (tests/test_gpu_parity.py, GPU).  What is recorded:
   block_small.npz     one MambaBlock: state dict, forward, gradients of every parameter and of
                       the input, and step() replayed over the same sequence (mamba.py:197-225,342-405)
   mamba_cfg1.npz      BASELINE config 1: Mamba(d_model=128, n_layers=2), B=8, L=64, fp32
+  block_ln.npz        the same as block_small for jamba's configuration, inner_layernorms=True (mamba.py:169-176,188-195)
+  block_odd.npz       the same for d_state=8, d_conv=5: shapes outside the fused kernels (pscan composition, cuDNN conv)
 """
 import os
 import sys
@@ -76,14 +78,16 @@ def gen_selscan(ref_mamba, out):
             out[f"{tag}_{k}"] = np32(v)
 
 
-def gen_block(ref_mamba, out):
-    torch.manual_seed(303)
-    cfg = ref_mamba.MambaConfig(d_model=16, n_layers=1)
+def gen_block(ref_mamba, out, seed=303, d_model=16, B=2, L=19, **cfg_kw):
+    torch.manual_seed(seed)
+    cfg = ref_mamba.MambaConfig(d_model=d_model, n_layers=1, **cfg_kw)
     blk = ref_mamba.MambaBlock(cfg)
     with torch.no_grad():   # move A_log / D off their special init so their gradients are exercised
         blk.A_log.add_(0.1 * torch.randn_like(blk.A_log))
         blk.D.add_(0.1 * torch.randn_like(blk.D))
-    B, L = 2, 19
+        for ln in (blk.dt_layernorm, blk.B_layernorm, blk.C_layernorm):
+            if ln is not None:   # RMSNorm weights start at one: move them too
+                ln.weight.add_(0.2 * torch.randn_like(ln.weight))
     x = torch.randn(B, L, cfg.d_model).requires_grad_()
     dy = torch.randn(B, L, cfg.d_model)
     y = blk(x)                                                           # mamba.py:197
@@ -125,11 +129,23 @@ def gen_cfg1(ref_mamba, out):
             out[f"grad.{k}"] = np32(v.grad)
 
 
+def gen_block_ln(ref_mamba, out):
+    gen_block(ref_mamba, out, seed=505, d_model=32, B=2, L=45, inner_layernorms=True)
+
+
+def gen_block_odd(ref_mamba, out):
+    gen_block(ref_mamba, out, seed=606, d_model=16, B=2, L=21, d_state=8, d_conv=5)
+
+
 def main():
     ref_mamba, ref_pscan = _load_reference()
     torch.set_num_threads(max(1, os.cpu_count() or 1))
+    only = set(sys.argv[1:])
     for name, fn, mod in (("pscan_small", gen_pscan, ref_pscan), ("selscan_small", gen_selscan, ref_mamba),
-                          ("block_small", gen_block, ref_mamba), ("mamba_cfg1", gen_cfg1, ref_mamba)):
+                          ("block_small", gen_block, ref_mamba), ("mamba_cfg1", gen_cfg1, ref_mamba),
+                          ("block_ln", gen_block_ln, ref_mamba), ("block_odd", gen_block_odd, ref_mamba)):
+        if only and name not in only:
+            continue
         out = {}
         fn(mod, out)
         path = os.path.join(HERE, name + ".npz")

@@ -200,9 +200,24 @@ def test_bench_helpers():
     fwd, bwd = bench.algorithmic_bytes(16, 4096, 1536, 2)
     assert fwd == 16 * 4096 * (4 * 1536 + 2 * 16) * 2 == 809500672
     assert bwd == 16 * 4096 * (7 * 1536 + 4 * 16) * 2 == 1417674752
-    t = bench.measured_traffic("cfg3", "selscan_bwd", 16)
-    assert t is None or t > bwd                      # checkpoints, saved y and the dB|dC rows ride on top of the algorithmic bytes
-    assert bench.measured_traffic("cfg3", "selscan_bwd", 3) is None and bench.measured_traffic("nope", "selscan_bwd", 16) is None
+    t, note = bench.measured_traffic("cfg3", "selscan_bwd", 16)
+    assert (t is None and "stale" in note) or t > bwd   # checkpoints, saved y and the dB|dC rows ride on top of the algorithmic bytes
+    assert bench.measured_traffic("cfg3", "selscan_bwd", 3)[0] is None and bench.measured_traffic("nope", "selscan_bwd", 16)[0] is None
+    # a capture is only quoted for the kernel sources it was taken from
+    import json, tempfile
+    real_root = bench.ROOT
+    with tempfile.TemporaryDirectory() as td:
+        os.makedirs(os.path.join(td, "profiles"))
+        rec = {"cfgX": {"batch_per_gpu": 4, "kernels": {"selscan_bwd": 123}, "source": "t", "source_hash": "deadbeef"}}
+        json.dump(rec, open(os.path.join(td, "profiles", "traffic.json"), "w"))
+        bench.ROOT = td
+        try:
+            assert bench.measured_traffic("cfgX", "selscan_bwd", 4)[0] is None          # hash of an empty tree differs
+            rec["cfgX"]["source_hash"] = bench.kernel_source_hash()
+            json.dump(rec, open(os.path.join(td, "profiles", "traffic.json"), "w"))
+            assert bench.measured_traffic("cfgX", "selscan_bwd", 4) == (123, "t")
+        finally:
+            bench.ROOT = real_root
 
 
 def test_numa_binding_is_a_no_op_without_topology():
