@@ -226,7 +226,7 @@ def sharded_parity_check(dist, dev, rank, world, by_channels):
     res = None
     if rank == 0:
         want = run(full["u"], full["delta"], full["z"], full["Bm"], full["Cm"], full["dout"], A_log, Dp, bias, False)
-        err = max(float((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-30)) for a, b in zip(gathered, want))
+        err = max(float((a.detach().float() - b.detach().float()).abs().max() / b.detach().float().abs().max().clamp_min(1e-30)) for a, b in zip(gathered, want))
         res = {"mode": "channels" if by_channels else "batch", "shape": [Bp, Lp, EDp], "max_rel_err": err, "tol": 1e-4, "ok": err < 1e-4}
     flag = torch.tensor([1 if (res is None or res["ok"]) else 0], device=dev)
     dist.broadcast(flag, 0)
