@@ -90,7 +90,7 @@ static const char *const kKernelNames[K_COUNT] = {
     "selscan_fwd_summary", "selscan_fwd", "selscan_bwd_summary", "selscan_bwd", "selscan_bwd_finalize_bc",
     "selscan_bwd_finalize_par", "pscan_fwd_summary", "pscan_fwd", "pscan_bwd_summary", "pscan_bwd",
     "conv1d_silu_fwd", "conv1d_silu_bwd", "conv1d_bwd_finalize", "conv1d_step", "ssm_step",
-    "add_rmsnorm_fwd", "add_rmsnorm_bwd", "add_rmsnorm_dw_finalize", "clip_adam_sumsq", "clip_adam_coef", "clip_adam_update"};
+    "add_rmsnorm_fwd", "add_rmsnorm_bwd", "add_rmsnorm_dw_finalize", "clip_adam_sumsq", "clip_adam_coef", "clip_adam_update", "add_mean_pool_fwd", "mean_pool_bwd"};
 
 void timing_mark(int id, cudaStream_t st, bool begin) {
     if (!g_timing_on.load(std::memory_order_relaxed)) return;

@@ -19,7 +19,7 @@ int sm_count();                       // SMs of the current device (148 on B200;
 enum KernelId {
     K_SELSCAN_FWD_SUMMARY = 0, K_SELSCAN_FWD, K_SELSCAN_BWD_SUMMARY, K_SELSCAN_BWD, K_SELSCAN_BWD_FIN_BC,
     K_SELSCAN_BWD_FIN_PAR, K_PSCAN_FWD_SUMMARY, K_PSCAN_FWD, K_PSCAN_BWD_SUMMARY, K_PSCAN_BWD,
-    K_CONV_FWD, K_CONV_BWD, K_CONV_BWD_FIN, K_CONV_STEP, K_SSM_STEP, K_ADDNORM_FWD, K_ADDNORM_BWD, K_ADDNORM_BWD_FIN, K_OPT_SUMSQ, K_OPT_COEF, K_OPT_ADAM, K_COUNT
+    K_CONV_FWD, K_CONV_BWD, K_CONV_BWD_FIN, K_CONV_STEP, K_SSM_STEP, K_ADDNORM_FWD, K_ADDNORM_BWD, K_ADDNORM_BWD_FIN, K_OPT_SUMSQ, K_OPT_COEF, K_OPT_ADAM, K_POOL_FWD, K_POOL_BWD, K_COUNT
 };
 void timing_mark(int id, cudaStream_t st, bool begin);
 struct ScopedKernelTimer {   // brackets one launch with events when timing is enabled

@@ -7,32 +7,38 @@
 //   forward : read A, X            write H          (12 B / element)
 //   backward: read A, dH, H        write dA, dX     (20 B / element)
 // Padding to a power of two is unnecessary (it is appended after L-1 and never changes [0, L)).
-// When B*D*N/4 threads cannot fill the GPU, L is split into segments: pass 1 reduces each segment to its
-// (product of A, local end state) pair, pass 2 starts each segment from the combined carry.
+// HBM needs ~12 MB of loads in flight; a launch has B*D*N*8*U bytes in flight (U = steps whose loads are issued before the
+// first is used), so small problems run the SAME single pass with narrower vectors and a deeper unroll -- (V, U) = (4, 8),
+// (2, 16), (1, 32): same registers, 1x / 2x / 4x the bytes in flight -- instead of paying a second pass.  Only when even
+// that cannot fill the GPU (B*D*N below ~25 k elements, e.g. one long sequence with few channels) is L split into segments:
+// pass 1 reduces each segment to its (product of A, local end state) pair, pass 2 starts each segment from the combined carry.
 #include "common.cuh"
 
 namespace gfe {
 
-constexpr int kPsUnroll = 8;
+constexpr int kPsUnrollMax = 32;
 
 struct PscanPlan {
     int nseg, seg_len;
+    int V, U;   // elements per thread, steps per load batch
 };
 
 static PscanPlan pscan_plan(int B, int L, int64_t DN) {
-    const int64_t nvec = (DN % 4 == 0) ? DN / 4 : DN;
-    const int64_t warps = ceil_div64((int64_t)B * nvec, 32);
-    const int64_t want = (int64_t)sm_count() * 16;
+    PscanPlan p;
+    const double target = 12e6 * sm_count() / 148.0;            // bytes in flight that saturate HBM (Little: ~6.5 TB/s x ~1.5 us)
+    const double per_u = (double)B * (double)DN * 8.0;          // forward: A and X, 4 bytes each, per unrolled step
+    p.V = 4; p.U = 8;
+    if (DN % 4 != 0 || per_u * 8 < target) { p.V = 2; p.U = 16; }
+    if (DN % 2 != 0 || per_u * 16 < target) { p.V = 1; p.U = 32; }
     int S = 1;
-    if (warps * 2 < want) {   // splitting re-reads A and X once more, only worth it when the GPU is less than half full
-        S = (int)ceil_div64(want, warps);
+    if (per_u * p.U * 2 < target) {   // still less than half of it: split L (re-reads A and X once more)
+        S = (int)(target / (per_u * p.U));
         const int max_by_len = L / 64;
         if (S > max_by_len) S = max_by_len;
         if (S > kMaxSeg) S = kMaxSeg;
         if (S < 1) S = 1;
     }
-    PscanPlan p;
-    p.seg_len = (int)ceil_div64(ceil_div64(L, S), kPsUnroll) * kPsUnroll;
+    p.seg_len = (int)ceil_div64(ceil_div64(L, S), kPsUnrollMax) * kPsUnrollMax;
     p.nseg = (int)ceil_div64(L, p.seg_len);
     return p;
 }
@@ -47,6 +53,14 @@ template <> struct Vec<4> {
     }
     static __device__ __forceinline__ float4 mul(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
     static __device__ __forceinline__ float4 add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+};
+template <> struct Vec<2> {
+    using type = float2;
+    static __device__ __forceinline__ float2 zero() { return make_float2(0.f, 0.f); }
+    static __device__ __forceinline__ float2 one() { return make_float2(1.f, 1.f); }
+    static __device__ __forceinline__ float2 fma(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+    static __device__ __forceinline__ float2 mul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+    static __device__ __forceinline__ float2 add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 };
 template <> struct Vec<1> {
     using type = float;
@@ -68,6 +82,7 @@ struct PscanParams {
 // ---- forward -----------------------------------------------------------------------------------------
 template <int V, bool SUMMARY>
 __global__ void __launch_bounds__(128) pscan_fwd_kernel(PscanParams p) {
+    constexpr int kPsUnroll = 32 / V;
     using VT = typename Vec<V>::type;
     const int64_t nvec = p.DN / V;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -85,22 +100,32 @@ __global__ void __launch_bounds__(128) pscan_fwd_kernel(PscanParams p) {
             h = Vec<V>::fma(reinterpret_cast<const VT *>(p.segP + o)[i], h, reinterpret_cast<const VT *>(p.segS + o)[i]);
         }
     }
-    for (int tb = t0; tb < t1; tb += kPsUnroll) {
-        VT a[kPsUnroll], x[kPsUnroll];
+    // two register buffers: the loads of batch k + 1 are in flight while batch k is consumed
+    VT a[2][kPsUnroll], x[2][kPsUnroll];
+    auto load = [&](int buf, int tb) {
 #pragma unroll
         for (int j = 0; j < kPsUnroll; ++j) {
             const int t = min(tb + j, t1 - 1);
-            a[j] = __ldcs(A + (size_t)t * nvec);
-            x[j] = __ldcs(X + (size_t)t * nvec);
+            a[buf][j] = __ldcs(A + (size_t)t * nvec);
+            x[buf][j] = __ldcs(X + (size_t)t * nvec);
         }
+    };
+    auto consume = [&](int buf, int tb) {
 #pragma unroll
         for (int j = 0; j < kPsUnroll; ++j) {
             if (tb + j < t1) {
-                h = Vec<V>::fma(a[j], h, x[j]);
-                if (SUMMARY) P = Vec<V>::mul(P, a[j]);
+                h = Vec<V>::fma(a[buf][j], h, x[buf][j]);
+                if (SUMMARY) P = Vec<V>::mul(P, a[buf][j]);
                 else __stcs(H + (size_t)(tb + j) * nvec, h);
             }
         }
+    };
+    if (t0 < t1) load(0, t0);
+    for (int tb = t0; tb < t1; tb += 2 * kPsUnroll) {
+        if (tb + kPsUnroll < t1) load(1, tb + kPsUnroll);
+        consume(0, tb);
+        if (tb + 2 * kPsUnroll < t1) load(0, tb + 2 * kPsUnroll);
+        if (tb + kPsUnroll < t1) consume(1, tb + kPsUnroll);
     }
     if (SUMMARY) {
         const size_t o = ((size_t)b * p.nseg + seg) * p.DN;
@@ -113,6 +138,7 @@ __global__ void __launch_bounds__(128) pscan_fwd_kernel(PscanParams p) {
 // G(t) = A[t] * g[t] is the carry handed to step t-1;  g[t] = dH[t] + G(t+1).
 template <int V, bool SUMMARY>
 __global__ void __launch_bounds__(128) pscan_bwd_kernel(PscanParams p) {
+    constexpr int kPsUnroll = 32 / V;
     using VT = typename Vec<V>::type;
     const int64_t nvec = p.DN / V;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -200,18 +226,21 @@ GFE_API int gfe_pscan_fwd(const float *A, const float *X, float *H, int B, int L
     p.segP = reinterpret_cast<float *>(ws);
     p.segS = reinterpret_cast<float *>(reinterpret_cast<char *>(ws) + need / 2);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const bool v4 = (DN % 4 == 0) && aligned16(A) && aligned16(X) && aligned16(H) && (need == 0 || aligned16(ws));
-    const int64_t nvec = v4 ? DN / 4 : DN;
+    const bool al = aligned16(A) && aligned16(X) && aligned16(H) && (need == 0 || aligned16(ws));
+    const int V = al ? pl.V : 1;                                  // rows of D*N fp32 keep 8 / 16-byte alignment when DN % V == 0
+    const int64_t nvec = DN / V;
     const dim3 block(128), grid((unsigned)ceil_div64(nvec, 128), pl.nseg, B);
     if (pl.nseg > 1) {
         { ScopedKernelTimer tm(K_PSCAN_FWD_SUMMARY, st);
-          if (v4) pscan_fwd_kernel<4, true><<<grid, block, 0, st>>>(p);
+          if (V == 4) pscan_fwd_kernel<4, true><<<grid, block, 0, st>>>(p);
+          else if (V == 2) pscan_fwd_kernel<2, true><<<grid, block, 0, st>>>(p);
           else pscan_fwd_kernel<1, true><<<grid, block, 0, st>>>(p); }
         rc = check_launch("pscan_fwd_summary");
         if (rc != GFE_OK) return rc;
     }
     { ScopedKernelTimer tm(K_PSCAN_FWD, st);
-      if (v4) pscan_fwd_kernel<4, false><<<grid, block, 0, st>>>(p);
+      if (V == 4) pscan_fwd_kernel<4, false><<<grid, block, 0, st>>>(p);
+      else if (V == 2) pscan_fwd_kernel<2, false><<<grid, block, 0, st>>>(p);
       else pscan_fwd_kernel<1, false><<<grid, block, 0, st>>>(p); }
     return check_launch("pscan_fwd");
 }
@@ -231,21 +260,23 @@ GFE_API int gfe_pscan_bwd(const float *A, const float *H, const float *dH, float
     p.segP = reinterpret_cast<float *>(ws);
     p.segS = reinterpret_cast<float *>(reinterpret_cast<char *>(ws) + need / 2);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const bool v4 = (DN % 4 == 0) && aligned16(A) && aligned16(H) && aligned16(dH) && aligned16(dA) && aligned16(dX) &&
-                    (need == 0 || aligned16(ws));
-    const int64_t nvec = v4 ? DN / 4 : DN;
+    const bool al = aligned16(A) && aligned16(H) && aligned16(dH) && aligned16(dA) && aligned16(dX) && (need == 0 || aligned16(ws));
+    const int V = al ? pl.V : 1;
+    const int64_t nvec = DN / V;
     const dim3 block(128);
     if (pl.nseg > 1) {
         const dim3 grid((unsigned)ceil_div64(nvec, 128), pl.nseg - 1, B);
         { ScopedKernelTimer tm(K_PSCAN_BWD_SUMMARY, st);
-          if (v4) pscan_bwd_kernel<4, true><<<grid, block, 0, st>>>(p);
+          if (V == 4) pscan_bwd_kernel<4, true><<<grid, block, 0, st>>>(p);
+          else if (V == 2) pscan_bwd_kernel<2, true><<<grid, block, 0, st>>>(p);
           else pscan_bwd_kernel<1, true><<<grid, block, 0, st>>>(p); }
         rc = check_launch("pscan_bwd_summary");
         if (rc != GFE_OK) return rc;
     }
     const dim3 grid((unsigned)ceil_div64(nvec, 128), pl.nseg, B);
     { ScopedKernelTimer tm(K_PSCAN_BWD, st);
-      if (v4) pscan_bwd_kernel<4, false><<<grid, block, 0, st>>>(p);
+      if (V == 4) pscan_bwd_kernel<4, false><<<grid, block, 0, st>>>(p);
+      else if (V == 2) pscan_bwd_kernel<2, false><<<grid, block, 0, st>>>(p);
       else pscan_bwd_kernel<1, false><<<grid, block, 0, st>>>(p); }
     return check_launch("pscan_bwd");
 }

@@ -90,6 +90,21 @@ class Mamba(nn.Module):
             branch = layer.mixer(normed)
         return branch + resid
 
+    def forward_mean(self, x):
+        """``torch.mean(self(x), dim=1, keepdim=True)`` -- what the classifier head does with the stack's output
+        (mamba_transformer.py:122-123) -- with the last residual add fused into the pooling: the (B, L, D) output is never
+        written.  Extension of the reference API; INTEGRATION.md shows the one-line caller change."""
+        if not x.is_cuda:
+            raise RuntimeError("gfe_mamba_b200.Mamba: CUDA tensors required (this library has no CPU fallback); "
+                               f"got input on {x.device}")
+        if len(self.layers) == 0 or not _fusable_norm(x, self.config):
+            return ops.add_mean_pool(self(x), None)
+        resid, branch = x, None
+        for layer in self.layers:
+            resid, normed = add_rmsnorm(resid, branch, layer.norm.weight, layer.norm.eps)
+            branch = layer.mixer(normed)
+        return ops.add_mean_pool(branch, resid)
+
     def step(self, x, caches):
         # x : (B, D); caches : [(h, inputs)] per layer
         for idx in range(len(self.layers)):

@@ -351,6 +351,48 @@ def add_rmsnorm(x: torch.Tensor, a: Optional[torch.Tensor], weight: torch.Tensor
     return _AddRMSNormFn.apply(x, a, weight, eps, torch.is_grad_enabled())
 
 
+# --------------------------------------------------------- final residual add + mean over L
+class _AddMeanPoolFn(torch.autograd.Function):
+    """mean over dim 1 of (a + r) -- the last residual add of the stack (cross_atten/mamba.py:103) fused with the head's
+    pooling (cross_atten/mamba_transformer.py:123).  SURVEY 8f rank 4."""
+
+    @staticmethod
+    def forward(ctx, a, r):
+        dev = _require_cuda(a, r)
+        if a.dim() != 3 or (r is not None and r.shape != a.shape):
+            raise ValueError("add_mean_pool: (B, L, D) operands of identical shape expected")
+        if a.dtype not in _DT:
+            raise TypeError(f"add_mean_pool: unsupported dtype {a.dtype}")
+        B, L, D = a.shape
+        a_ = a.detach().contiguous()
+        r_ = None if r is None else r.detach().to(a.dtype).contiguous()
+        out = torch.empty((B, 1, D), dtype=a.dtype, device=dev)
+        l = nat.lib()
+        with torch.cuda.device(dev):
+            nws = l.gfe_add_mean_pool_workspace_bytes(B, L, D)
+            ws = _bytes(nws, dev)
+            nat.check(l.gfe_add_mean_pool_fwd(_ptr(a_), _ptr(r_), _ptr(out), B, L, D, _DT[a.dtype], _ptr(ws), nws, _stream(dev)),
+                      "add_mean_pool_fwd")
+        ctx.shape, ctx.has_r = (B, L, D), r is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, L, D = ctx.shape
+        dev = dout.device
+        d_ = dout.detach().contiguous()
+        da = torch.empty((B, L, D), dtype=d_.dtype, device=dev)
+        l = nat.lib()
+        with torch.cuda.device(dev):
+            nat.check(l.gfe_mean_pool_bwd(_ptr(d_), _ptr(da), B, L, D, _DT[d_.dtype], _stream(dev)), "mean_pool_bwd")
+        return da, (da if ctx.has_r else None)
+
+
+def add_mean_pool(a: torch.Tensor, r: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(B, 1, D) = mean over L of (a + r); a, r: (B, L, D).  Equals ``torch.mean(a + r, dim=1, keepdim=True)``."""
+    return _AddMeanPoolFn.apply(a, r)
+
+
 # ------------------------------------------------------------------------------- decode step
 def _no_autograd(name: str, *ts):
     """The decode kernels have no backward: refuse to silently detach a graph (MambaBlock.step falls back to the

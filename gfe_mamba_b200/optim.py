@@ -62,6 +62,9 @@ class ClipAdam(torch.optim.Optimizer):
         if cached is not None and cached[0] == key:
             return cached[1]
         dev = params[0].device
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("ClipAdam: the parameter/gradient tables must exist before a CUDA-graph capture (their upload and the "
+                               "step counter's initialisation would be replayed): run one step with the same gradient buffers first")
         for p in params:
             if p.device != dev or p.dtype != torch.float32 or p.grad.dtype != torch.float32 \
                     or not p.is_contiguous() or not p.grad.is_contiguous():

@@ -159,6 +159,16 @@ GFE_API int gfe_add_rmsnorm_bwd(const void *resid, const float *w, const float *
                                 void *dx, float *dw, int64_t rows, int D, int dtype, void *ws, size_t ws_bytes,
                                 void *stream);
 
+/* ------------------------------------ final residual add + mean over L (head) --
+ * out[b, d] = mean_t (a[b, t, d] + r[b, t, d]): the last residual add of the Mamba stack (mamba.py:103) fused with the
+ * classifier head's pooling (mamba_transformer.py:123, torch.mean(x, dim=1)).  a, r: contiguous (B, L, D), r may be NULL;
+ * out: (B, D), same dtype.  bwd: da[b, t, d] = dout[b, d] / L (the gradient of both operands).
+ */
+GFE_API size_t gfe_add_mean_pool_workspace_bytes(int B, int L, int D);
+GFE_API int gfe_add_mean_pool_fwd(const void *a, const void *r, void *out, int B, int L, int D, int dtype, void *ws, size_t ws_bytes,
+                                  void *stream);
+GFE_API int gfe_mean_pool_bwd(const void *dout, void *da, int B, int L, int D, int dtype, void *stream);
+
 /* ------------------------------------------- multi-tensor clip + Adam step --
  * One optimiser step for a whole parameter list in three launches; replaces the per-parameter loop
  *     for p in params: torch.nn.utils.clip_grad_norm_(p, max_norm)      (classify_mamba.py:106-107)

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
     lib = _native.lib()                      # also checks every signature in the ctypes table resolves
     assert set(_native.SIGNATURES) == set(_declared_symbols())
     assert lib.gfe_version() == 100
-    assert lib.gfe_timing_kernel_count() == 21 and lib.gfe_timing_kernel_name(3) == b"selscan_bwd"
+    assert lib.gfe_timing_kernel_count() == 23 and lib.gfe_timing_kernel_name(3) == b"selscan_bwd"
 
 
 def test_size_queries_without_gpu():

@@ -84,3 +84,70 @@ def test_clip_adam_zero_grad_and_graph_capture():
     torch.cuda.synchronize()
     for p, q in zip(ours, ref):
         assert torch.allclose(p, q, rtol=2e-6, atol=2e-7), (p - q).abs().max().item()
+
+
+# ------------------------------------------------------------------------------------------- head pooling
+@pytest.mark.parametrize("B,L,D,dtype,with_r", [(2, 1858, 512, torch.float32, True), (3, 65, 96, torch.float32, False),
+                                                (4, 1000, 768, torch.bfloat16, True)])
+def test_add_mean_pool_vs_torch(B, L, D, dtype, with_r):
+    """mean over L of (a + r): the stack's last residual add fused with mamba_transformer.py:123, forward and backward."""
+    from gfe_mamba_b200 import add_mean_pool
+    g = torch.Generator(device="cuda").manual_seed(B * L)
+    a = torch.randn(B, L, D, device="cuda", generator=g).to(dtype).requires_grad_()
+    r = torch.randn(B, L, D, device="cuda", generator=g).to(dtype).requires_grad_() if with_r else None
+    dout = torch.randn(B, 1, D, device="cuda", generator=g).to(dtype)
+    out = add_mean_pool(a, r)
+    out.backward(dout)
+    a64 = a.detach().double().requires_grad_()
+    r64 = r.detach().double().requires_grad_() if with_r else None
+    ref = torch.mean(a64 + r64 if with_r else a64, dim=1, keepdim=True)
+    ref.backward(dout.double())
+    tol = 1e-6 if dtype == torch.float32 else 1e-2
+    assert out.shape == (B, 1, D) and out.dtype == dtype
+    assert float((out.double() - ref).abs().max() / ref.abs().max()) < tol
+    assert float((a.grad.double() - a64.grad).abs().max() / a64.grad.abs().max()) < tol
+    if with_r:
+        assert float((r.grad.double() - r64.grad).abs().max() / r64.grad.abs().max()) < tol
+
+
+def test_mamba_forward_mean_matches_forward_then_mean():
+    from gfe_mamba_b200 import Mamba, MambaConfig
+    torch.manual_seed(4)
+    model = Mamba(MambaConfig(d_model=64, n_layers=2)).cuda()
+    x = torch.randn(2, 77, 64, device="cuda")
+    x1, x2 = x.clone().requires_grad_(), x.clone().requires_grad_()
+    y1 = torch.mean(model(x1), dim=1, keepdim=True)
+    y1.square().sum().backward()
+    g1 = [p.grad.clone() for p in model.parameters()]
+    model.zero_grad()
+    y2 = model.forward_mean(x2)
+    y2.square().sum().backward()
+    assert torch.allclose(y1, y2, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(x1.grad, x2.grad, rtol=1e-4, atol=1e-6)
+    for a, p in zip(g1, model.parameters()):
+        assert torch.allclose(a, p.grad, rtol=1e-4, atol=1e-6)
+
+
+# -------------------------------------------------------------------------------------- whole training step, eager vs graph
+def test_graphed_train_step_matches_eager():
+    """GraphedTrainStep replays forward + backward + ClipAdam from one CUDA graph: same parameters as the eager steps."""
+    from gfe_mamba_b200 import ClipAdam, Mamba, MambaConfig
+    from gfe_mamba_b200.train import GraphedTrainStep, TrainStep
+    xs = [torch.randn(2, 130, 64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(i)) for i in range(5)]
+
+    def build():
+        torch.manual_seed(7)
+        m = Mamba(MambaConfig(d_model=64, n_layers=2)).cuda()
+        return m, TrainStep(m, ClipAdam(m.parameters(), lr=1e-3, max_norm=1.0, zero_grad=True))
+
+    m1, s1 = build()
+    m2, s2 = build()
+    for _ in range(3):                         # GraphedTrainStep warms up with 3 eager steps on its example input (they build
+        s1(xs[0])                              # the optimiser tables and the launch caches OUTSIDE the capture): same here
+    g = GraphedTrainStep(s2, xs[0], warmup=3)
+    losses1 = [float(s1(x)) for x in xs]
+    losses2 = [float(g(x)) for x in xs]
+    torch.cuda.synchronize()
+    assert all(abs(a - b) <= 1e-5 * max(1.0, abs(a)) for a, b in zip(losses1, losses2)), (losses1, losses2)
+    for p, q in zip(m1.parameters(), m2.parameters()):
+        assert torch.allclose(p, q, rtol=1e-4, atol=1e-6)

@@ -102,9 +102,11 @@ def test_pscan_golden(golden_dir, L):
     assert relerr(A.grad, g[f"L{L}_dA"]) < 1e-5
 
 
-@pytest.mark.parametrize("shape", [(2, 1858, 8, 16), (32, 256, 64, 16), (1, 4096, 4, 16), (3, 100, 5, 3), (2, 777, 7, 1)])
+@pytest.mark.parametrize("shape", [(2, 1858, 8, 16), (32, 256, 64, 16), (1, 4096, 4, 16), (3, 100, 5, 3), (2, 777, 7, 1),
+                                   (8, 300, 1024, 16), (16, 128, 1024, 16), (2, 1858, 1024, 16)])
 def test_pscan_vs_oracle(shape):
-    """Random shapes incl. non-power-of-two L, the L-split path (small B*D*N), odd D*N (scalar path)."""
+    """Random shapes incl. non-power-of-two L, the L-split path (small B*D*N), odd D*N (scalar path), and sizes that select
+    each single-pass variant: 1 / 2 / 4 elements per thread with 32 / 16 / 8 steps of loads in flight."""
     from gfe_mamba_b200 import pscan
     r = np.random.default_rng(7)
     A = r.uniform(0.3, 1.0, shape).astype(np.float32)

@@ -74,6 +74,12 @@ res = {"op": "Mamba stack training step (fwd + bwd + grad all-reduce + clip + Ad
        "optimizer": "torch Adam + per-parameter clip_grad_norm_ loop" if a.torch_optim else "ClipAdam (3 launches)",
        "ms_per_step": round(ms_step, 3), "tokens_per_s": round(world * a.batch * a.seq / ms_step * 1e3),
        "library_kernels_ms": round(sum(lib_ms.values()), 3), "library_kernels_ms_per_step": lib_ms}
+if world > 1:   # replicas must stay identical: same parameters on every rank after the synchronised steps (checked BEFORE the
+    # measurement below that deliberately runs steps without the collectives)
+    chk = torch.stack([p.detach().double().abs().sum() for p in model.parameters()]).sum().reshape(1)
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    res["replicas_identical"] = bool((hi - lo).abs().item() <= 1e-9 * max(1.0, abs(hi.item())))
 if not a.graph:
     ms_fb = timed(lambda: (step.forward_backward(x), sync.zero() if sync else [p.grad.zero_() for p in model.parameters()]), a.steps)
     res["fwd_bwd_ms"] = round(ms_fb, 3)
@@ -86,11 +92,6 @@ if world > 1:
                 "allreduce_total_ms": round(ms_ar, 3), "step_without_allreduce_ms": round(ms_nosync, 3),
                 "allreduce_exposed_ms": round(max(ms_step - ms_nosync, 0.0), 3),
                 "allreduce_hidden_ms": round(max(ms_ar - max(ms_step - ms_nosync, 0.0), 0.0), 3)})
-    # replicas must stay identical: same parameters on every rank after the steps
-    chk = torch.stack([p.detach().float().sum() for p in model.parameters()]).sum().reshape(1).double()
-    lo, hi = chk.clone(), chk.clone()
-    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-    res["replicas_identical"] = bool((hi - lo).abs().item() <= 1e-6 * max(1.0, abs(hi.item())))
 if rank == 0:
     print(json.dumps(res), file=real_stdout, flush=True)
 if world > 1:
