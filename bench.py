@@ -255,7 +255,7 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default=None, choices=[None, "f32", "bf16", "f16"])
     ap.add_argument("--e2e-steps", type=int, default=10)
-    ap.add_argument("--e2e-rows", type=int, default=0, help="batch rows per pipeline chunk of the e2e leg (0 = B/4)")
+    ap.add_argument("--e2e-rows", type=int, default=0, help="batch rows per pipeline chunk of the e2e leg (0 = B/8)")
     ap.add_argument("--batch", type=int, default=0, help="override the workload's per-GPU batch (A/B measurements)")
     ap.add_argument("--shard", default="batch", choices=["batch", "channels"],
                     help="N > 1: batch = every rank its own B rows (weak scaling); channels = ONE batch, rank g owns ED/N channels, "

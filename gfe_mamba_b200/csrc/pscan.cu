@@ -100,32 +100,22 @@ __global__ void __launch_bounds__(128) pscan_fwd_kernel(PscanParams p) {
             h = Vec<V>::fma(reinterpret_cast<const VT *>(p.segP + o)[i], h, reinterpret_cast<const VT *>(p.segS + o)[i]);
         }
     }
-    // two register buffers: the loads of batch k + 1 are in flight while batch k is consumed
-    VT a[2][kPsUnroll], x[2][kPsUnroll];
-    auto load = [&](int buf, int tb) {
+    for (int tb = t0; tb < t1; tb += kPsUnroll) {   // (double-buffered load batches were measured slower: 150+ registers)
+        VT a[kPsUnroll], x[kPsUnroll];
 #pragma unroll
         for (int j = 0; j < kPsUnroll; ++j) {
             const int t = min(tb + j, t1 - 1);
-            a[buf][j] = __ldcs(A + (size_t)t * nvec);
-            x[buf][j] = __ldcs(X + (size_t)t * nvec);
+            a[j] = __ldcs(A + (size_t)t * nvec);
+            x[j] = __ldcs(X + (size_t)t * nvec);
         }
-    };
-    auto consume = [&](int buf, int tb) {
 #pragma unroll
         for (int j = 0; j < kPsUnroll; ++j) {
             if (tb + j < t1) {
-                h = Vec<V>::fma(a[buf][j], h, x[buf][j]);
-                if (SUMMARY) P = Vec<V>::mul(P, a[buf][j]);
+                h = Vec<V>::fma(a[j], h, x[j]);
+                if (SUMMARY) P = Vec<V>::mul(P, a[j]);
                 else __stcs(H + (size_t)(tb + j) * nvec, h);
             }
         }
-    };
-    if (t0 < t1) load(0, t0);
-    for (int tb = t0; tb < t1; tb += 2 * kPsUnroll) {
-        if (tb + kPsUnroll < t1) load(1, tb + kPsUnroll);
-        consume(0, tb);
-        if (tb + 2 * kPsUnroll < t1) load(0, tb + 2 * kPsUnroll);
-        if (tb + kPsUnroll < t1) consume(1, tb + kPsUnroll);
     }
     if (SUMMARY) {
         const size_t o = ((size_t)b * p.nseg + seg) * p.DN;

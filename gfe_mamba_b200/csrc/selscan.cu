@@ -872,7 +872,7 @@ GFE_API size_t gfe_selscan_ckpt_bytes_dt(int B, int L, int ED, int N, int dtype)
     if (dtype != GFE_F32 && dtype != GFE_BF16 && dtype != GFE_F16) return 0;
     // segment-start states (fp32) + y before the gate in the activation dtype
     const size_t ybytes = (size_t)B * L * ED * (dtype == GFE_F32 ? 4 : 2);
-    if (gfe::chain_applicable(B, L, ED)) return gfe::chain_ckpt_state_bytes(B, L, ED) + ybytes;
+    if (gfe::chain_applicable(B, L, ED)) return gfe::chain_ckpt_state_bytes(B, L, ED, dtype) + ybytes;
     return gfe::ckpt_state_bytes(B, L, ED) + ybytes;
 }
 

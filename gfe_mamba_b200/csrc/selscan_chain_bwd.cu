@@ -46,7 +46,8 @@ struct BwdChainSmem {
     static constexpr int kTile = kChunk * CPC * (int)sizeof(T);         // one of u, delta, dout, y, z
     static constexpr int kNTile = HAS_Z ? 5 : 3;
     static constexpr int kBCRaw = kChunk * kNState * (int)sizeof(T);     // one of B, C
-    static constexpr int kCk = CPC * kNState * 4;                        // the checkpoints of one half chunk: [c][16] fp32
+    using CK = typename CkptOf<T>::type;
+    static constexpr int kCk = CPC * kNState * (int)sizeof(CK);          // the checkpoints of one half chunk: [c][16]
     static constexpr int kOffCk = kNTile * kTile + 2 * kBCRaw;           // inside a stage: both halves' checkpoints
     static constexpr int kStage = kOffCk + 2 * kCk;
     static constexpr int kSPlane = NP + 2;                               // float4 per (t, quad) plane of the partials (+32 B skew)
@@ -70,7 +71,8 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
     constexpr int BCP = kChunk * kNState * (int)sizeof(T) / 16;   // pieces per B (or C) tile: 32 (16-bit), 64 (fp32)
     constexpr int BCI = (2 * BCP + NT - 1) / NT;      // B|C pieces per thread
     constexpr int BCC = kChunk * 8 / NT;              // fp32 B|C quads converted per thread
-    constexpr int CKP = 2 * SM::kCk / 16 / NT;        // 16-byte checkpoint pieces per thread and chunk (4)
+    using CK = typename SM::CK;
+    constexpr int CKP = 2 * SM::kCk / 16 / NT;        // 16-byte checkpoint pieces per thread and chunk (4 fp32, 2 bf16)
     constexpr int SPL = SM::kSPlane;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rp = tid >> 2, rq = tid & 3;     // recurrence mapping: channel pair in block, state quad
@@ -123,9 +125,9 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
         const T *Bb = reinterpret_cast<const T *>(p.Bm) + (int64_t)b * p.B_bs;
         const T *Cb = reinterpret_cast<const T *>(p.Cm) + (int64_t)b * p.C_bs;
         // checkpoints [b][t / 8][c][16] fp32: the block's CPC channels of one half chunk are contiguous (staged with the tiles)
-        const char *ckb = reinterpret_cast<const char *>(reinterpret_cast<const float *>(p.ckpt) +
+        const char *ckb = reinterpret_cast<const char *>(reinterpret_cast<const CK *>(p.ckpt) +
                                                          ((size_t)b * p.nchunks * p.ED + c0) * kNState);
-        const size_t ck_step = (size_t)p.ED * kNState * sizeof(float);   // bytes between consecutive checkpoints
+        const size_t ck_step = (size_t)p.ED * kNState * sizeof(CK);      // bytes between consecutive checkpoints
         T *dub = reinterpret_cast<T *>(p.du) + (int64_t)b * p.du_bs + c0 + 2 * cp;
         T *ddb = reinterpret_cast<T *>(p.ddelta) + (int64_t)b * p.dd_bs + c0 + 2 * cp;
         T *dzb = HAS_Z ? reinterpret_cast<T *>(p.dz) + (int64_t)b * p.dz_bs + c0 + 2 * ip : nullptr;
@@ -334,8 +336,8 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
 #endif
 #pragma unroll
                 for (int ch = 0; ch < 2; ++ch) {
-                    const float4 ck = *(reinterpret_cast<const float4 *>(smem + stage * SM::kStage + SM::kOffCk + half * SM::kCk) +
-                                        (2 * rp + ch) * (kNState / 4) + rq);
+                    const float4 ck = ckpt_load_smem(reinterpret_cast<const CK *>(smem + stage * SM::kStage + SM::kOffCk + half * SM::kCk) +
+                                                     (2 * rp + ch) * kNState + 4 * rq);
                     h0[ch][0] = sw ? make_float2(ck.y, ck.x) : make_float2(ck.x, ck.y);
                     h1[ch][0] = sw ? make_float2(ck.w, ck.z) : make_float2(ck.z, ck.w);
                 }

@@ -129,8 +129,9 @@ int chain_check_alignment(const gfe_selscan_args *a) {
     return GFE_OK;
 }
 
-size_t chain_ckpt_state_bytes(int B, int L, int ED) {   // [b][t / 8][c][16] fp32
-    return (size_t)B * ((L + kCkptV2 - 1) / kCkptV2) * ED * kNState * sizeof(float);
+size_t chain_ckpt_state_bytes(int B, int L, int ED, int dtype) {   // [b][t / 8][c][16], fp32 (bf16 for bf16 activations), 256-byte padded
+    const size_t el = (GFE_CKPT_BF16 && dtype == GFE_BF16) ? 2 : 4;
+    return align_up((size_t)B * ((L + kCkptV2 - 1) / kCkptV2) * ED * kNState * el, 256);
 }
 
 void chain_fill_params(ScanParams &p, const gfe_selscan_args *a) {
@@ -142,7 +143,7 @@ void chain_fill_params(ScanParams &p, const gfe_selscan_args *a) {
     p.z_bs = a->z_bs; p.z_rs = a->z_rs; p.B_bs = a->B_bs; p.B_rs = a->B_rs; p.C_bs = a->C_bs; p.C_rs = a->C_rs;
     p.A_log = a->A_log; p.D = a->D; p.dt_bias = a->dt_bias;
     p.ckpt = reinterpret_cast<float2 *>(a->ckpt);
-    p.ysave = a->ckpt ? reinterpret_cast<char *>(a->ckpt) + chain_ckpt_state_bytes(a->batch, a->seqlen, a->d_inner) : nullptr;
+    p.ysave = a->ckpt ? reinterpret_cast<char *>(a->ckpt) + chain_ckpt_state_bytes(a->batch, a->seqlen, a->d_inner, a->dtype) : nullptr;
     p.G = a->d_inner / 32;
 }
 

@@ -4,6 +4,10 @@
 
 #include "common.cuh"
 
+#ifndef GFE_CKPT_BF16
+#define GFE_CKPT_BF16 1        // chained kernels: bf16 activations keep their 8-step state checkpoints in bf16 (half the checkpoint stream)
+#endif
+
 namespace gfe {
 
 struct ScanParams {
@@ -184,6 +188,25 @@ __device__ __forceinline__ float2 softplus_pair(float2 x, float2 &sig) {
 #endif
 }
 
+// Element type of the chained kernels' state checkpoints: fp32, except bf16 for bf16 activations (the recomputed states then
+// carry a 2^-9 relative error, well inside the 2e-2 tolerance of that dtype; fp16 keeps fp32 checkpoints: states can exceed
+// its range).
+template <typename T> struct CkptOf { using type = float; };
+#if GFE_CKPT_BF16
+template <> struct CkptOf<__nv_bfloat16> { using type = __nv_bfloat16; };
+#endif
+__device__ __forceinline__ void ckpt_store(float *dst, float4 v) { __stcs(reinterpret_cast<float4 *>(dst), v); }
+__device__ __forceinline__ void ckpt_store(__nv_bfloat16 *dst, float4 v) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    __stcs(reinterpret_cast<uint2 *>(dst), make_uint2(*reinterpret_cast<const uint32_t *>(&lo), *reinterpret_cast<const uint32_t *>(&hi)));
+}
+__device__ __forceinline__ float4 ckpt_load_smem(const float *src) { return *reinterpret_cast<const float4 *>(src); }
+__device__ __forceinline__ float4 ckpt_load_smem(const __nv_bfloat16 *src) {
+    const uint2 r = *reinterpret_cast<const uint2 *>(src);
+    const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&r.x)), hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&r.y));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
 // ---- chained-unit plumbing -----------------------------------------------------------------------------
 __device__ __forceinline__ int ld_acquire(const int *p) {
     int v;
@@ -298,7 +321,7 @@ static int persistent_grid(int nt, size_t smem, int total) {
 #define GFE_CBWD_MINB 2        // backward: CTAs of 128 threads per SM the register budget is set for (2: 255 registers, 3: 168)
 #endif
 bool chain_applicable(int B, int L, int ED);              // shape-only: both directions take the same decision
-size_t chain_ckpt_state_bytes(int B, int L, int ED);
+size_t chain_ckpt_state_bytes(int B, int L, int ED, int dtype);
 size_t chain_fwd_workspace_bytes(int B, int L, int ED);
 size_t chain_bwd_workspace_bytes(int B, int L, int ED);
 int chain_launch_fwd(const gfe_selscan_args *a, cudaStream_t st);

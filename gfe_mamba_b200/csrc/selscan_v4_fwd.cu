@@ -11,8 +11,8 @@
 //     computed once per unit, and the per-(t, channel pair) scalar work runs once per pair in the item mapping;
 //   * per lane and step: 3 LDS.128 + 16 packed FP32 ops + 8 exp2 (2 of them on the FMA pipe) + 1 STS.64 for 8
 //     state-steps (v2: 3 LDS.128 + 8 + 4 + 1 for 4).
-// Segment chaining (ChainSched), checkpoint layout ([b][t/8][c][16] fp32) and the saved y are exactly those of v2, so
-// the v2 backward kernel consumes what this kernel writes.
+// Segment chaining (ChainSched); checkpoints [b][t/8][c][16] (fp32, bf16 for bf16 activations) and the saved y are what
+// selscan_chain_bwd.cu consumes.
 #include "common.cuh"
 #include "selscan_shared.cuh"
 
@@ -50,10 +50,10 @@ struct FwdV4Smem {
 // The 16 recurrence steps of one chunk, with the slot loads software-pipelined by hand: neither nvcc nor ptxas moves the
 // three LDS of step j + 1 above the partial-sum STS of step j (may-alias shared addresses; __restrict__ does not reach
 // ptxas), so in source order every step waited out a full LDS latency before its first FMUL2 (seen in the SASS).
-template <int CPC>
+template <int CPC, typename CK>
 __device__ __forceinline__ void v4_recur_chunk(const float4 *__restrict__ dd_r, const float4 *__restrict__ bc_r,
                                                float2 *__restrict__ y_w, const float2 (&A2)[2][2], float2 (&h)[2][2],
-                                               float4 *__restrict__ ckq, size_t ck_step, int tb, int t1) {
+                                               CK *__restrict__ ckq, size_t ck_step, int tb, int t1) {
     constexpr int kV4YPlane = CPC / 2 + 4;
     constexpr int PF = GFE_V4_PREFETCH;   // slot loads are issued PF steps ahead of their use, BEFORE the stores of the steps between
     float4 dd_q[PF + 1], B_q[PF + 1], C_q[PF + 1];
@@ -67,9 +67,9 @@ __device__ __forceinline__ void v4_recur_chunk(const float4 *__restrict__ dd_r, 
             C_q[PF] = bc_r[(j + PF) * 8 + 4];
         }
         if (j % kCkptV2 == 0 && ckq != nullptr && tb + j < t1) {   // states before step tb + j, for backward
-            float4 *dst = ckq + (size_t)((tb + j) / kCkptV2) * ck_step;
-            __stcs(dst, make_float4(h[0][0].x, h[0][0].y, h[0][1].x, h[0][1].y));
-            __stcs(dst + kNState / 4, make_float4(h[1][0].x, h[1][0].y, h[1][1].x, h[1][1].y));
+            CK *dst = ckq + (size_t)((tb + j) / kCkptV2) * ck_step;
+            ckpt_store(dst, make_float4(h[0][0].x, h[0][0].y, h[0][1].x, h[0][1].y));
+            ckpt_store(dst + kNState, make_float4(h[1][0].x, h[1][0].y, h[1][1].x, h[1][1].y));
         }
         const float4 dd = dd_q[0], B4 = B_q[0], C4 = C_q[0];
 #pragma unroll
@@ -143,9 +143,9 @@ __global__ void __launch_bounds__(2 * CPC, GFE_V4_MINB * (64 / CPC)) selscan_fwd
         T *ob = reinterpret_cast<T *>(p.out) + (int64_t)b * p.o_bs + c0 + 2 * ip;
         T *yb = p.ysave ? reinterpret_cast<T *>(p.ysave) + (int64_t)b * p.L * p.ED + c0 + 2 * ip : nullptr;
         // checkpoints [b][t / 8][c][16] fp32: this lane's quads of channels 2 rp and 2 rp + 1
-        float4 *ckq = p.ckpt ? reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.ckpt) +
-                                                          ((size_t)b * p.nchunks * p.ED + c0 + 2 * rp) * kNState) + rq : nullptr;
-        const size_t ck_step = (size_t)p.ED * (kNState / 4);
+        using CK = typename CkptOf<T>::type;
+        CK *ckq = p.ckpt ? reinterpret_cast<CK *>(p.ckpt) + ((size_t)b * p.nchunks * p.ED + c0 + 2 * rp) * kNState + 4 * rq : nullptr;
+        const size_t ck_step = (size_t)p.ED * kNState;   // elements between consecutive checkpoints
 
         // per-thread source pointers of the staged pieces at row t0 (advanced by 16 rows per chunk)
         const char *su, *sd, *sz = nullptr, *sbc[BCI];
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(2 * CPC, GFE_V4_MINB * (64 / CPC)) selscan_fwd
         for (int k = 0; k < nch; ++k) {
             const int tb = t0 + k * kChunk;
             __syncthreads();   // (1) slots of chunk k are complete
-            v4_recur_chunk<CPC>(dd_r, bc_r, y_w, A2, h, ckq, ck_step, tb, t1);   // 16 steps of this lane's 2 x 4 states
+            v4_recur_chunk<CPC, CK>(dd_r, bc_r, y_w, A2, h, ckq, ck_step, tb, t1);   // 16 steps of this lane's 2 x 4 states
             cp_async_wait<NST - 2>();   // chunk k + 1 has landed (this thread's pieces)
             __syncthreads();            // (2) partial sums complete; chunk k + 1 visible; stage k % NST free
             issue(k + NST, stage);

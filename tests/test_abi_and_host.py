@@ -46,8 +46,9 @@ def test_size_queries_without_gpu():
     assert lib.gfe_selscan_ckpt_bytes(B, L, ED, N) == states + B * L * ED * 4
     assert lib.gfe_selscan_ckpt_bytes(1, 65536, 1024, N) == (65536 // 16) * 1024 * N * 4 + 65536 * 1024 * 4   # L-split path: 16
     assert lib.gfe_selscan_ckpt_bytes(B, L, ED, 8) == 0            # unsupported d_state -> 0
-    # y before the gate is kept in the activation dtype: bf16 halves that part
-    assert lib.gfe_selscan_ckpt_bytes_dt(B, L, ED, N, _native.GFE_BF16) == states + B * L * ED * 2
+    # bf16 activations: bf16 state checkpoints and y before the gate in bf16 -- half of everything saved for backward
+    assert lib.gfe_selscan_ckpt_bytes_dt(B, L, ED, N, _native.GFE_BF16) == states // 2 + B * L * ED * 2 <= 0.61e9
+    assert lib.gfe_selscan_ckpt_bytes_dt(B, L, ED, N, _native.GFE_F16) == states + B * L * ED * 2     # fp16 keeps fp32 states (range)
     assert lib.gfe_selscan_ckpt_bytes_dt(B, L, ED, N, _native.GFE_F32) == lib.gfe_selscan_ckpt_bytes(B, L, ED, N)
     # one dB|dC row (32 fp32) per (channel block of <= 64 channels, token)
     assert (ED // 64) * B * L * 32 * 4 <= lib.gfe_selscan_bwd_workspace_bytes(B, L, ED, N) < (ED // 32) * B * L * 32 * 4
