@@ -33,7 +33,7 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 constexpr int kNState = 16;     // d_state the fused kernels are compiled for
 constexpr int kChunk = 16;      // time steps per register chunk == checkpoint interval
-constexpr int kMaxSeg = 64;     // max L-split factor
+constexpr int kMaxSeg = 256;    // max L-split factor (one long sequence sharded over 8 GPUs: 128 channels, 256 segments of 256 steps)
 constexpr int kCkptV2 = 8;      // checkpoint interval of the chained (v2) kernels: halves the register-resident history of backward
 
 // How one (b, channel) sequence is split along L when B*ED alone cannot fill the GPU.

@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(128) selscan_fwd_kernel(ScanParams p) {
     for (int q = 0; q < kPairs; ++q) h[q] = make_float2(0.f, 0.f);
 
     // carry-in: combine the summaries of all earlier segments (exp of a delta prefix sum per state)
+#pragma unroll 4
     for (int s = 0; s < seg; ++s) {
         const float sd = p.seg_sd[(size_t)(b * p.nseg + s) * p.ED + c];
         const float2 *src = p.seg_h + ((size_t)(b * p.nseg + s) * kPairs) * p.ED + c;
@@ -415,6 +416,7 @@ __global__ void __launch_bounds__(128) selscan_bwd_kernel(ScanParams p) {
             sdA[q * 32 + lane] = make_float2(0.f, 0.f);
         }
         // carry-in from the later segments: G = P[s] * G + Gloc[s], s = nseg-1 .. seg+1
+#pragma unroll 4
         for (int s = p.nseg - 1; s > seg; --s) {
             const float sd = p.seg_sd[(size_t)(b * p.nseg + s) * p.ED + c];
             const float2 *src = p.seg_h + ((size_t)(b * p.nseg + s) * kPairs) * p.ED + c;

@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(128) selscan_fwd_fast_kernel(ScanParams p) {
     }
 #pragma unroll
     for (int q = 0; q < NP; ++q) h[q] = make_float2(0.f, 0.f);
+#pragma unroll 4   // the loads of four segments are in flight together: the summaries come from L2 and the loop is latency-bound
     for (int s = 0; s < seg; ++s) {   // carry-in from earlier segments
         const float sd = p.seg_sd[(size_t)(b * p.nseg + s) * p.ED + c];
         const float2 *src = p.seg_h + ((size_t)(b * p.nseg + s) * kPairs + half * NP) * p.ED + c;
@@ -330,6 +331,7 @@ __global__ void __launch_bounds__(128) selscan_bwd_fast_kernel(ScanParams p) {
             sG[q * 32 + lane] = make_float2(0.f, 0.f);
             sdA[q * 32 + lane] = make_float2(0.f, 0.f);
         }
+#pragma unroll 4
         for (int s = p.nseg - 1; s > seg; --s) {
             const float sd = p.seg_sd[(size_t)(b * p.nseg + s) * p.ED + c];
             const float2 *src = p.seg_h + ((size_t)(b * p.nseg + s) * kPairs + half * NP) * p.ED + c;

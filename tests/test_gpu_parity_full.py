@@ -52,6 +52,7 @@ def _oracle(t, d0):
 @pytest.mark.parametrize("name,B,L,ED,dt", [
     ("cfg3", 16, 4096, 1536, torch.bfloat16),    # BASELINE configs[2], full batch: dA_log / ddt_bias sum 65 536 tokens
     ("cfg4", 1, 65536, 1024, torch.float32),     # BASELINE configs[3], full length: 64-segment L-split backward
+    ("cfg4-shard8", 1, 65536, 128, torch.float32),   # one rank's channel shard of configs[3] at 8 GPUs: 256 L-segments
     ("prod", 2, 1858, 1024, torch.float32),      # production shape at its real width
     ("cfg5-rows", 40, 1024, 1024, torch.float32),   # BASELINE configs[4] scan shape, 40 of its 256 rows (chained, multi-unit)
 ])
