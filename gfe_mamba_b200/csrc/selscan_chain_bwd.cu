@@ -588,8 +588,7 @@ static int launch_bwd_chain_t(const gfe_selscan_args *a, cudaStream_t st) {
         ScopedKernelTimer tm(K_SELSCAN_BWD, st);
         const bool hz = a->z != nullptr;
         if (cpc == 64) launch_bwd_chain_cpc<T, 64>(p, cs, hz, cpb, st);
-        else if (cpc == 32) launch_bwd_chain_cpc<T, 32>(p, cs, hz, cpb, st);
-        else launch_bwd_chain_cpc<T, 16>(p, cs, hz, cpb, st);
+        else launch_bwd_chain_cpc<T, 32>(p, cs, hz, cpb, st);   // (16-channel blocks measured slower; not instantiated)
     }
     rc = check_launch("selscan_bwd (chained)");
     if (rc != GFE_OK) return rc;

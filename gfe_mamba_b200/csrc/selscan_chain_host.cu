@@ -30,25 +30,25 @@ static void chain_plan(int B, int L, int nblk, int ctas_per_sm, int &nseg, int &
     nseg = (L + seg_len - 1) / seg_len;
 }
 
-// Channel-block width of the forward kernel.  Narrow blocks (one warp per CTA) decouple the warps of an SM completely;
-// the width only has to divide ED.
+// Channel-block width: 64 when it divides ED, else 32 (16 / 32 / 64 measured on cfg3 and cfg5: 64 is never slower,
+// profiles/r02_chain_variants.txt).
 static int fwd_cpc(int ED) {
 #ifdef GFE_EXPERIMENTS
     if (const char *e = getenv("GFE_FWD_CPC")) {   // A/B measurements only
         const int v = atoi(e);
-        if ((v == 16 || v == 32 || v == 64) && ED % v == 0) return v;
+        if ((v == 32 || v == 64) && ED % v == 0) return v;
     }
 #endif
-    return ED % GFE_FWD_CPC_DEFAULT == 0 ? GFE_FWD_CPC_DEFAULT : (ED % 32 == 0 ? 32 : 16);
+    return ED % GFE_FWD_CPC_DEFAULT == 0 ? GFE_FWD_CPC_DEFAULT : 32;
 }
 static int bwd_cpc(int ED) {
 #ifdef GFE_EXPERIMENTS
     if (const char *e = getenv("GFE_BWD_CPC")) {
         const int v = atoi(e);
-        if ((v == 16 || v == 32 || v == 64) && ED % v == 0) return v;
+        if ((v == 32 || v == 64) && ED % v == 0) return v;
     }
 #endif
-    return ED % GFE_BWD_CPC_DEFAULT == 0 ? GFE_BWD_CPC_DEFAULT : (ED % 32 == 0 ? 32 : 16);
+    return ED % GFE_BWD_CPC_DEFAULT == 0 ? GFE_BWD_CPC_DEFAULT : 32;
 }
 
 void chain_fwd_plan(int B, int L, int ED, int &cpc, int &nblk, int &nseg, int &seg_len) {
@@ -62,10 +62,10 @@ void chain_bwd_plan(int B, int L, int ED, int &cpc, int &nblk, int &nseg, int &s
     chain_plan(B, L, nblk, GFE_CBWD_MINB * (64 / cpc), nseg, seg_len);
 }
 
-// The chained kernels serve every shape with ED % 16 == 0 that offers enough (row, channel) parallelism to fill the GPU
+// The chained kernels serve every shape with ED % 32 == 0 that offers enough (row, channel) parallelism to fill the GPU
 // without splitting L; smaller problems take the L-split pair (selscan.cu), which recomputes instead of waiting.
 bool chain_applicable(int B, int L, int ED) {
-    if (ED % 16 != 0) return false;
+    if (ED % 32 != 0) return false;
 #ifdef GFE_EXPERIMENTS
     if (const char *e = getenv("GFE_SELSCAN_CHAIN")) {   // A/B measurements only
         if (e[0] == '0') return false;

@@ -83,3 +83,29 @@ def _worker(rank, world, port, mode):
 @pytest.mark.parametrize("mode", ["channel", "batch"])
 def test_two_gpu_sharding_matches_single_gpu(mode):
     mp.spawn(_worker, args=(2, _free_port(), mode), nprocs=2, join=True)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_one_process_two_devices_same_shape():
+    """One host thread runs the same shapes on cuda:0 and then cuda:1: the launch caches (dynamic-shared-memory opt-in,
+    persistent grid size, workspace sizes) are per device, so the second device must not inherit the first one's."""
+    from gfe_mamba_b200 import Mamba, MambaConfig
+    shapes = [(24, 203, 512), (2, 300, 64)]          # chained kernels (57-88 KB of dynamic shared memory) and the L-split pair
+    ref = {}
+    for di in (0, 1):
+        dev = torch.device("cuda", di)
+        for (B, L, ED) in shapes:
+            d = _inputs(B, L, ED, 16, dev)
+            out, g = _full(d)
+            torch.cuda.synchronize(dev)
+            key = (B, L, ED)
+            if di == 0:
+                ref[key] = (out.cpu(), {k: v.cpu() for k, v in g.items()})
+            else:
+                assert _rel(out.cpu(), ref[key][0]) < 1e-6
+                for k, v in g.items():
+                    assert _rel(v.cpu(), ref[key][1][k]) < 1e-5, (key, k)
+        torch.manual_seed(0)
+        m = Mamba(MambaConfig(d_model=64, n_layers=2)).to(dev)
+        y = m(torch.randn(2, 50, 64, device=dev))
+        assert torch.isfinite(y).all()
