@@ -60,8 +60,18 @@ struct BwdChainSmem {
     static constexpr int kTotal = kOffRed + NW * kChunk * kCRedRow * 4;
 };
 
+#ifdef GFE_PHASE_CLOCKS   // development only: cycles per phase, summed over warp leaders (tools/dbg/phase_clocks.py)
+__device__ unsigned long long g_bwd_phase_clk[8];
+#define GFE_CLK(i) do { const long long now_ = clock64(); if ((threadIdx.x & 31) == 0) clk_acc[i] += now_ - clk_last; clk_last = now_; } while (0)
+#else
+#define GFE_CLK(i) do { } while (0)
+#endif
+
 template <typename T, bool HAS_Z, int CPB, int CPC>
 __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_bwd_chain_kernel(ScanParams p, ChainSched cs) {
+#ifdef GFE_PHASE_CLOCKS
+    long long clk_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, clk_last = clock64();
+#endif
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_unit;
     using SM = BwdChainSmem<T, HAS_Z, CPC>;
@@ -311,15 +321,18 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
             }
         };
 
+        GFE_CLK(0);   // unit set-up (incl. waiting for the successor segment's carry)
         cp_async_wait<NST - 1>();
         __syncthreads();
         phase_a(0, 0);
+        GFE_CLK(5);
 
         int stage = 0;   // i % NST
         for (int i = 0; i < nch; ++i) {
             const int k = klast - i;
             const int tb = k * kChunk;
             __syncthreads();   // (1) slots of this chunk are complete
+            GFE_CLK(1);
 
 #pragma unroll 1
             for (int half = 1; half >= 0; --half) {   // steps 8..15, then 0..7 (one copy of the sweep code)
@@ -430,6 +443,7 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
                 }
 
                 // ------------------------------------------------------------ phase C (this warp's 8 pairs x 8 steps)
+                GFE_CLK(2);
                 __syncwarp();
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
@@ -452,10 +466,12 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
                     }
                 }
                 __syncwarp();   // the next half overwrites the partial planes
+                GFE_CLK(6);
             }
 
             cp_async_wait<NST - 2>();
             __syncthreads();   // (2) per-warp dB|dC rows complete; next chunk visible; this chunk's stage free
+            GFE_CLK(3);
             issue(i + NST, stage);
             stage = stage + 1 == NST ? 0 : stage + 1;
             // dB|dC rows of this CTA: add the warps' tiles; row layout {dB[n], dC[n]} interleaved
@@ -474,7 +490,9 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
                     __stcs(reinterpret_cast<float4 *>(p.part_bc + (((size_t)blk * p.B + b) * p.L + tb + t) * 32) + q8, acc);
                 }
             }
+            GFE_CLK(4);
             if (i + 1 < nch) phase_a(i + 1, stage);
+            GFE_CLK(5);
         }
 
         // ---- end of unit: parameter-gradient partials, carry-out ----
@@ -513,8 +531,21 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
             if (tid == 0) st_release(cs.flags + unit, 1);
         }
         cp_async_wait<0>();
+        GFE_CLK(7);
     }
+#ifdef GFE_PHASE_CLOCKS
+    if ((threadIdx.x & 31) == 0)
+        for (int i = 0; i < 8; ++i) atomicAdd(&g_bwd_phase_clk[i], (unsigned long long)clk_acc[i]);
+#endif
 }
+
+#ifdef GFE_PHASE_CLOCKS
+extern "C" __attribute__((visibility("default"))) int gfe_debug_bwd_phase_clocks(unsigned long long *out, int reset) {
+    if (out) cudaMemcpyFromSymbol(out, g_bwd_phase_clk, sizeof(g_bwd_phase_clk));
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_bwd_phase_clk, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------------- host
 struct BwdWs {

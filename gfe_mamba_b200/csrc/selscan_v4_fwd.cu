@@ -93,8 +93,18 @@ __device__ __forceinline__ void v4_recur_chunk(const float4 *__restrict__ dd_r, 
     }
 }
 
+#ifdef GFE_PHASE_CLOCKS   // development only: cycles per phase, summed over warp leaders (tools/dbg/phase_clocks.py)
+__device__ unsigned long long g_fwd_phase_clk[8];
+#define GFE_CLK(i) do { const long long now_ = clock64(); if ((threadIdx.x & 31) == 0) clk_acc[i] += now_ - clk_last; clk_last = now_; } while (0)
+#else
+#define GFE_CLK(i) do { } while (0)
+#endif
+
 template <typename T, bool HAS_Z, int CPB, int CPC>
 __global__ void __launch_bounds__(2 * CPC, GFE_V4_MINB * (64 / CPC)) selscan_fwd_v4_kernel(ScanParams p, ChainSched cs) {
+#ifdef GFE_PHASE_CLOCKS
+    long long clk_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, clk_last = clock64();
+#endif
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_unit;
     using SM = FwdV4Smem<T, HAS_Z, CPC>;
@@ -287,9 +297,11 @@ __global__ void __launch_bounds__(2 * CPC, GFE_V4_MINB * (64 / CPC)) selscan_fwd
             for (int i = 0; i < BCC; ++i) sBC[tid + i * NT] = bcv[i];
         };
 
+        GFE_CLK(0);   // unit set-up (incl. waiting for the predecessor segment)
         cp_async_wait<NST - 1>();
         __syncthreads();
         phase_a(0, 0);
+        GFE_CLK(5);
         // running output pointers of this thread's item rows (row ir of the current chunk)
         T *op = ob + (int64_t)(t0 + ir) * p.o_rs;
         T *yp_g = yb != nullptr ? yb + (int64_t)(t0 + ir) * p.ED : nullptr;
@@ -299,9 +311,12 @@ __global__ void __launch_bounds__(2 * CPC, GFE_V4_MINB * (64 / CPC)) selscan_fwd
         for (int k = 0; k < nch; ++k) {
             const int tb = t0 + k * kChunk;
             __syncthreads();   // (1) slots of chunk k are complete
+            GFE_CLK(1);
             v4_recur_chunk<CPC, CK>(dd_r, bc_r, y_w, A2, h, ckq, ck_step, tb, t1);   // 16 steps of this lane's 2 x 4 states
+            GFE_CLK(2);
             cp_async_wait<NST - 2>();   // chunk k + 1 has landed (this thread's pieces)
             __syncthreads();            // (2) partial sums complete; chunk k + 1 visible; stage k % NST free
+            GFE_CLK(3);
             issue(k + NST, stage);
             stage = stage + 1 == NST ? 0 : stage + 1;
 
@@ -320,7 +335,9 @@ __global__ void __launch_bounds__(2 * CPC, GFE_V4_MINB * (64 / CPC)) selscan_fwd
                 op += o_step;
                 if (yp_g != nullptr) yp_g += y_step;
             }
+            GFE_CLK(4);
             if (k + 1 < nch) phase_a(k + 1, stage);
+            GFE_CLK(5);
         }
 
         // carry-out / final state
@@ -340,8 +357,21 @@ __global__ void __launch_bounds__(2 * CPC, GFE_V4_MINB * (64 / CPC)) selscan_fwd
             if (tid == 0) st_release(cs.flags + unit, 1);
         }
         cp_async_wait<0>();
+        GFE_CLK(6);
     }
+#ifdef GFE_PHASE_CLOCKS
+    if ((threadIdx.x & 31) == 0)
+        for (int i = 0; i < 8; ++i) atomicAdd(&g_fwd_phase_clk[i], (unsigned long long)clk_acc[i]);
+#endif
 }
+
+#ifdef GFE_PHASE_CLOCKS
+extern "C" __attribute__((visibility("default"))) int gfe_debug_fwd_phase_clocks(unsigned long long *out, int reset) {
+    if (out) cudaMemcpyFromSymbol(out, g_fwd_phase_clk, sizeof(g_fwd_phase_clk));
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_fwd_phase_clk, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------------- host
 template <typename T, bool HAS_Z, int CPB, int CPC>
