@@ -391,6 +391,24 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
     ms_per_step = elapsed_ms / args.steps
+    # the step's collective alone (nothing to overlap with), reported next to the step: dB|dC under channel sharding, the
+    # parameter-gradient bucket under batch sharding
+    allreduce_ms = None
+    if world > 1:
+        n_el = 2 * B * L * N_STATE if by_channels else ED * N_STATE + 2 * ED
+        buf = torch.zeros(n_el, device=dev, dtype=torch.float32)
+        for _ in range(3):
+            dist.all_reduce(buf)
+        sync_all()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(20):
+            dist.all_reduce(buf)
+        a1.record()
+        sync_all()
+        t = torch.tensor([a0.elapsed_time(a1) / 20], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        allreduce_ms = {"ms": round(float(t.item()), 4), "bytes": 4 * n_el, "what": "dB|dC (fp32)" if by_channels else "A_log, D, dt_bias gradients (fp32)"}
     tokens_per_s = (1 if by_channels else world) * B * L / (ms_per_step * 1e-3)   # channel sharding: ONE batch of tokens
 
     # ---- roofline of the dominant kernel + every kernel's share
@@ -466,6 +484,8 @@ def main():
                 "kernels": kern_list}
         if parity is not None:
             line["parity_check"] = parity
+        if allreduce_ms is not None:
+            line["allreduce"] = allreduce_ms
         print(json.dumps(line), file=out_stream, flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -7,11 +7,15 @@
 //   forward : read A, X            write H          (12 B / element)
 //   backward: read A, dH, H        write dA, dX     (20 B / element)
 // Padding to a power of two is unnecessary (it is appended after L-1 and never changes [0, L)).
-// HBM needs ~12 MB of loads in flight; a launch has B*D*N*8*U bytes in flight (U = steps whose loads are issued before the
-// first is used), so small problems run the SAME single pass with narrower vectors and a deeper unroll -- (V, U) = (4, 8),
-// (2, 16), (1, 32): same registers, 1x / 2x / 4x the bytes in flight -- instead of paying a second pass.  Only when even
+// HBM needs ~12 MB of loads in flight; a launch has B*D*N*4*nloads*U bytes in flight (U = steps whose loads are issued before
+// the first is used), so small problems run the SAME single pass with narrower vectors and a deeper unroll -- forward (V, U)
+// = (4, 16) or (1, 32), backward (4, 8), (2, 16) or (1, 32), chosen from measurements (profiles/r02_pscan.txt) -- instead of
+// paying a second pass.  Only when even
 // that cannot fill the GPU (B*D*N below ~25 k elements, e.g. one long sequence with few channels) is L split into segments:
 // pass 1 reduces each segment to its (product of A, local end state) pair, pass 2 starts each segment from the combined carry.
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gfe {
@@ -23,13 +27,26 @@ struct PscanPlan {
     int V, U;   // elements per thread, steps per load batch
 };
 
-static PscanPlan pscan_plan(int B, int L, int64_t DN) {
+// nloads = tensors read per step: 2 forward (A, X), 3 backward (A, dH, H): backward reaches the same bytes in flight with
+// fewer steps, so it keeps the wider vectors longer (measured at B=8, L=1024, D=1024: (4, 8) 98 % of the HBM peak, (2, 16) 88 %).
+static PscanPlan pscan_plan(int B, int L, int64_t DN, int nloads) {
     PscanPlan p;
-    const double target = 12e6 * sm_count() / 148.0;            // bytes in flight that saturate HBM (Little: ~6.5 TB/s x ~1.5 us)
-    const double per_u = (double)B * (double)DN * 8.0;          // forward: A and X, 4 bytes each, per unrolled step
-    p.V = 4; p.U = 8;
-    if (DN % 4 != 0 || per_u * 8 < target) { p.V = 2; p.U = 16; }
-    if (DN % 2 != 0 || per_u * 16 < target) { p.V = 1; p.U = 32; }
+    double target = 12e6 * sm_count() / 148.0;                  // bytes in flight that saturate HBM (Little: ~6.5 TB/s x ~1.5 us)
+#ifdef GFE_EXPERIMENTS
+    if (const char *e = getenv("GFE_PSCAN_TARGET_MB")) target = atof(e) * 1e6;   // A/B measurements only
+#endif
+    const double per_u = (double)B * (double)DN * 4.0 * nloads;  // bytes requested per unrolled step
+    if (nloads == 2) {   // forward: (4, 16) when that alone fills the pipe, else the narrowest vectors and the deepest unroll
+        p.V = 4; p.U = 16;
+        if (DN % 4 != 0 || per_u * 16 < target) { p.V = 1; p.U = 32; }
+    } else {             // backward
+        p.V = 4; p.U = 8;
+        if (DN % 4 != 0 || per_u * 8 < target) { p.V = 2; p.U = 16; }
+        if (DN % 2 != 0 || per_u * 16 < target) { p.V = 1; p.U = 32; }
+    }
+#ifdef GFE_EXPERIMENTS
+    if (const char *e = getenv("GFE_PSCAN_VU")) { int v = 0, u = 0; if (sscanf(e, "%d,%d", &v, &u) == 2 && nloads == 2) { p.V = v; p.U = u; } }
+#endif
     int S = 1;
     if (per_u * p.U * 2 < target) {   // still less than half of it: split L (re-reads A and X once more)
         S = (int)(target / (per_u * p.U));
@@ -80,9 +97,9 @@ struct PscanParams {
 };
 
 // ---- forward -----------------------------------------------------------------------------------------
-template <int V, bool SUMMARY>
+template <int V, int U, bool SUMMARY>
 __global__ void __launch_bounds__(128) pscan_fwd_kernel(PscanParams p) {
-    constexpr int kPsUnroll = 32 / V;
+    constexpr int kPsUnroll = U;
     using VT = typename Vec<V>::type;
     const int64_t nvec = p.DN / V;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -126,9 +143,9 @@ __global__ void __launch_bounds__(128) pscan_fwd_kernel(PscanParams p) {
 
 // ---- backward ----------------------------------------------------------------------------------------
 // G(t) = A[t] * g[t] is the carry handed to step t-1;  g[t] = dH[t] + G(t+1).
-template <int V, bool SUMMARY>
+template <int V, int U, bool SUMMARY>
 __global__ void __launch_bounds__(128) pscan_bwd_kernel(PscanParams p) {
-    constexpr int kPsUnroll = 32 / V;
+    constexpr int kPsUnroll = U;
     using VT = typename Vec<V>::type;
     const int64_t nvec = p.DN / V;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -197,7 +214,7 @@ extern "C" {
 GFE_API size_t gfe_pscan_workspace_bytes(int B, int L, int D, int N) {
     if (B <= 0 || L <= 0 || D <= 0 || N <= 0) return 0;
     const int64_t DN = (int64_t)D * N;
-    const gfe::PscanPlan pl = gfe::pscan_plan(B, L, DN);
+    const gfe::PscanPlan pl = gfe::pscan_plan(B, L, DN, 2);   // the forward plan never has fewer segments than the backward plan
     if (pl.nseg <= 1) return 0;
     return 2 * gfe::align_up((size_t)B * pl.nseg * DN * sizeof(float), 256);
 }
@@ -208,7 +225,7 @@ GFE_API int gfe_pscan_fwd(const float *A, const float *X, float *H, int B, int L
     int rc = pscan_check(A, X, H, B, L, D, N);
     if (rc != GFE_OK) return rc;
     const int64_t DN = (int64_t)D * N;
-    const PscanPlan pl = pscan_plan(B, L, DN);
+    const PscanPlan pl = pscan_plan(B, L, DN, 2);
     const size_t need = gfe_pscan_workspace_bytes(B, L, D, N);
     if (need > 0 && (ws == nullptr || ws_bytes < need)) { set_error("pscan_fwd: workspace too small (%zu < %zu)", ws ? ws_bytes : (size_t)0, need); return GFE_ERR_WORKSPACE; }
     PscanParams p{};
@@ -220,18 +237,21 @@ GFE_API int gfe_pscan_fwd(const float *A, const float *X, float *H, int B, int L
     const int V = al ? pl.V : 1;                                  // rows of D*N fp32 keep 8 / 16-byte alignment when DN % V == 0
     const int64_t nvec = DN / V;
     const dim3 block(128), grid((unsigned)ceil_div64(nvec, 128), pl.nseg, B);
+    const bool deep = pl.U == 16;   // (4, 16): twice the loads in flight at the widest request
     if (pl.nseg > 1) {
         { ScopedKernelTimer tm(K_PSCAN_FWD_SUMMARY, st);
-          if (V == 4) pscan_fwd_kernel<4, true><<<grid, block, 0, st>>>(p);
-          else if (V == 2) pscan_fwd_kernel<2, true><<<grid, block, 0, st>>>(p);
-          else pscan_fwd_kernel<1, true><<<grid, block, 0, st>>>(p); }
+          if (V == 4 && deep) pscan_fwd_kernel<4, 16, true><<<grid, block, 0, st>>>(p);
+          else if (V == 4) pscan_fwd_kernel<4, 8, true><<<grid, block, 0, st>>>(p);
+          else if (V == 2) pscan_fwd_kernel<2, 16, true><<<grid, block, 0, st>>>(p);
+          else pscan_fwd_kernel<1, 32, true><<<grid, block, 0, st>>>(p); }
         rc = check_launch("pscan_fwd_summary");
         if (rc != GFE_OK) return rc;
     }
     { ScopedKernelTimer tm(K_PSCAN_FWD, st);
-      if (V == 4) pscan_fwd_kernel<4, false><<<grid, block, 0, st>>>(p);
-      else if (V == 2) pscan_fwd_kernel<2, false><<<grid, block, 0, st>>>(p);
-      else pscan_fwd_kernel<1, false><<<grid, block, 0, st>>>(p); }
+      if (V == 4 && deep) pscan_fwd_kernel<4, 16, false><<<grid, block, 0, st>>>(p);
+      else if (V == 4) pscan_fwd_kernel<4, 8, false><<<grid, block, 0, st>>>(p);
+      else if (V == 2) pscan_fwd_kernel<2, 16, false><<<grid, block, 0, st>>>(p);
+      else pscan_fwd_kernel<1, 32, false><<<grid, block, 0, st>>>(p); }
     return check_launch("pscan_fwd");
 }
 
@@ -242,7 +262,7 @@ GFE_API int gfe_pscan_bwd(const float *A, const float *H, const float *dH, float
     if (rc != GFE_OK) return rc;
     if (!dA || !dX) { set_error("pscan_bwd: NULL output pointer"); return GFE_ERR_ARG; }
     const int64_t DN = (int64_t)D * N;
-    const PscanPlan pl = pscan_plan(B, L, DN);
+    const PscanPlan pl = pscan_plan(B, L, DN, 3);
     const size_t need = gfe_pscan_workspace_bytes(B, L, D, N);
     if (need > 0 && (ws == nullptr || ws_bytes < need)) { set_error("pscan_bwd: workspace too small (%zu < %zu)", ws ? ws_bytes : (size_t)0, need); return GFE_ERR_WORKSPACE; }
     PscanParams p{};
@@ -257,17 +277,17 @@ GFE_API int gfe_pscan_bwd(const float *A, const float *H, const float *dH, float
     if (pl.nseg > 1) {
         const dim3 grid((unsigned)ceil_div64(nvec, 128), pl.nseg - 1, B);
         { ScopedKernelTimer tm(K_PSCAN_BWD_SUMMARY, st);
-          if (V == 4) pscan_bwd_kernel<4, true><<<grid, block, 0, st>>>(p);
-          else if (V == 2) pscan_bwd_kernel<2, true><<<grid, block, 0, st>>>(p);
-          else pscan_bwd_kernel<1, true><<<grid, block, 0, st>>>(p); }
+          if (V == 4) pscan_bwd_kernel<4, 8, true><<<grid, block, 0, st>>>(p);
+          else if (V == 2) pscan_bwd_kernel<2, 16, true><<<grid, block, 0, st>>>(p);
+          else pscan_bwd_kernel<1, 32, true><<<grid, block, 0, st>>>(p); }
         rc = check_launch("pscan_bwd_summary");
         if (rc != GFE_OK) return rc;
     }
     const dim3 grid((unsigned)ceil_div64(nvec, 128), pl.nseg, B);
     { ScopedKernelTimer tm(K_PSCAN_BWD, st);
-      if (V == 4) pscan_bwd_kernel<4, false><<<grid, block, 0, st>>>(p);
-      else if (V == 2) pscan_bwd_kernel<2, false><<<grid, block, 0, st>>>(p);
-      else pscan_bwd_kernel<1, false><<<grid, block, 0, st>>>(p); }
+      if (V == 4) pscan_bwd_kernel<4, 8, false><<<grid, block, 0, st>>>(p);
+      else if (V == 2) pscan_bwd_kernel<2, 16, false><<<grid, block, 0, st>>>(p);
+      else pscan_bwd_kernel<1, 32, false><<<grid, block, 0, st>>>(p); }
     return check_launch("pscan_bwd");
 }
 
