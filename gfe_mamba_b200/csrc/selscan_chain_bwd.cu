@@ -474,6 +474,7 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
             GFE_CLK(3);
             issue(i + NST, stage);
             stage = stage + 1 == NST ? 0 : stage + 1;
+            GFE_CLK(7);   // (debug build: the refill alone; the unit tail is not clocked then)
             // dB|dC rows of this CTA: add the warps' tiles; row layout {dB[n], dC[n]} interleaved
 #pragma unroll
             for (int q = 0; q < BCC; ++q) {
@@ -531,7 +532,7 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
             if (tid == 0) st_release(cs.flags + unit, 1);
         }
         cp_async_wait<0>();
-        GFE_CLK(7);
+        GFE_CLK(0);
     }
 #ifdef GFE_PHASE_CLOCKS
     if ((threadIdx.x & 31) == 0)

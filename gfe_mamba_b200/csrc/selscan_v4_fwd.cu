@@ -319,6 +319,7 @@ __global__ void __launch_bounds__(2 * CPC, GFE_V4_MINB * (64 / CPC)) selscan_fwd
             GFE_CLK(3);
             issue(k + NST, stage);
             stage = stage + 1 == NST ? 0 : stage + 1;
+            GFE_CLK(7);   // (debug build: the refill alone)
 
             // ---- per-(t, channel pair) epilogue of chunk k: sum the 4 quads, D skip, gate, store ----
 #pragma unroll
