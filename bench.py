@@ -57,7 +57,7 @@ def measured_peaks():
 
 
 KERNEL_SOURCES = ("selscan_v4_fwd.cu", "selscan_chain_bwd.cu", "selscan_chain_host.cu", "selscan_shared.cuh", "selscan.cu",
-                  "selscan_fast.cuh", "common.cuh")
+                  "selscan_seg.cu", "common.cuh")
 
 
 def kernel_source_hash():

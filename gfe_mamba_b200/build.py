@@ -20,7 +20,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 OBJDIR = os.path.join(PKG, "build")
 LIB = os.path.join(LIBDIR, "libgfe_mamba_b200.so")
-SOURCES = ["api.cu", "selscan.cu", "selscan_chain_host.cu", "selscan_v4_fwd.cu", "selscan_chain_bwd.cu", "pscan.cu", "conv1d.cu", "step.cu", "addnorm.cu", "optim.cu", "pool.cu"]
+SOURCES = ["api.cu", "selscan.cu", "selscan_chain_host.cu", "selscan_v4_fwd.cu", "selscan_chain_bwd.cu", "selscan_seg.cu", "pscan.cu", "conv1d.cu", "step.cu", "addnorm.cu", "optim.cu", "pool.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -54,17 +54,6 @@ SegPlan plan_segments(int B, int L, int ED) {
     p.nchunks = (L + kChunk - 1) / kChunk;
     const int64_t smsp = (int64_t)sm_count() * 4;
     const int64_t nwarps = (int64_t)B * ((ED + 31) / 32);
-    // Two lanes per channel double the warp count of the fast kernels (needs ED % 32 == 0).  Measured on cfg3
-    // (1.3 warps per scheduler at P = 1): forward gains 30 %, backward does not (per-chunk overhead doubles),
-    // so backward only switches when it cannot even give every scheduler one warp.
-    p.p_fwd = (ED % 32 == 0 && nwarps < 2 * smsp) ? 2 : 1;
-    p.p_bwd = (ED % 32 == 0 && nwarps < smsp) ? 2 : 1;
-#ifdef GFE_EXPERIMENTS
-    if (const char *e = getenv("GFE_SELSCAN_P")) {   // A/B measurements only
-        if (e[0] == '1') p.p_fwd = p.p_bwd = 1;
-        if (e[0] == '2' && ED % 32 == 0) p.p_fwd = p.p_bwd = 2;
-    }
-#endif
     int S = 1;
     if (nwarps * 2 < smsp) {
         S = (int)ceil_div64(2 * smsp, nwarps);

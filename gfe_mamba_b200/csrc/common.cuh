@@ -41,7 +41,6 @@ struct SegPlan {
     int nseg;     // S: number of segments (1 = no split, single pass)
     int seg_len;  // steps per segment, multiple of kChunk
     int nchunks;  // ceil(L / kChunk)
-    int p_fwd, p_bwd;  // lanes per channel of the fast kernels: 2 when B*ED/32 warps cannot fill the schedulers
 };
 SegPlan plan_segments(int B, int L, int ED);
 

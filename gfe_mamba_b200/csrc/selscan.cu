@@ -609,41 +609,9 @@ __global__ void __launch_bounds__(128) selscan_bwd_finalize_par_kernel(ScanParam
     }
 }
 
-}  // namespace gfe
-
-#include "selscan_fast.cuh"
-
-namespace gfe {
-
 // =====================================================================================================
 // Host side
 // =====================================================================================================
-
-// cp.async granularity usable for this call: 16 (all bases/strides 16-byte aligned), 4, or 0 (generic kernels).
-static int fast_path_cpb(const gfe_selscan_args *a, bool bwd) {
-    if (a->d_inner % 32 != 0) return 0;
-    const int64_t s = a->dtype == GFE_F32 ? 4 : 2;
-    const void *ptrs[6] = {a->u, a->delta, a->z, a->Bm, a->Cm, bwd ? a->dout : nullptr};
-    const int64_t strides[12] = {a->u_bs, a->u_rs, a->delta_bs, a->delta_rs, a->z ? a->z_bs : 0, a->z ? a->z_rs : 0,
-                                 a->B_bs, a->B_rs, a->C_bs, a->C_rs, bwd ? a->dout_bs : 0, bwd ? a->dout_rs : 0};
-    bool ok16 = true, ok4 = true;
-    for (const void *q : ptrs) {
-        const uintptr_t v = reinterpret_cast<uintptr_t>(q);
-        ok16 &= (v & 15) == 0;
-        ok4 &= (v & 3) == 0;
-    }
-    for (int64_t st : strides) {
-        ok16 &= (st * s) % 16 == 0;
-        ok4 &= (st * s) % 4 == 0;
-    }
-#ifdef GFE_EXPERIMENTS
-    if (const char *e = getenv("GFE_SELSCAN_PATH")) {   // A/B measurements only (experiments build)
-        if (!strcmp(e, "generic")) return 0;
-        if (!strcmp(e, "cp4")) ok16 = false;
-    }
-#endif
-    return ok16 ? 16 : (ok4 ? 4 : 0);
-}
 
 static int warps_per_cta() { return 1; }
 
@@ -666,7 +634,7 @@ static WsLayout fwd_ws_layout(int B, int L, int ED, const SegPlan &sp) {
 static WsLayout bwd_ws_layout(int B, int L, int ED, const SegPlan &sp) {
     WsLayout w = fwd_ws_layout(B, L, ED, sp);
     size_t off = w.total;
-    const size_t G = (ED + 15) / 16;   // channel groups of the finest decomposition (P = 2: 16 channels per warp)
+    const size_t G = (ED + 31) / 32;   // one dB|dC row per warp (32 channels) and token
     w.part_bc = off;
     off += align_up(G * B * L * 32 * sizeof(float), 256);
     w.part_par = off;
@@ -748,28 +716,7 @@ static int launch_fwd(const gfe_selscan_args *a, cudaStream_t st) {
         int rc = check_launch("selscan_fwd_summary");
         if (rc != GFE_OK) return rc;
     }
-    const int cpb = fast_path_cpb(a, false);
-    if (cpb != 0) {
-        const bool hz = a->z != nullptr;
-        const int P = sp.p_fwd;
-        const int Gf = a->d_inner / (32 / P);
-        const dim3 gridf((Gf + W - 1) / W, sp.nseg, a->batch);
-        ScopedKernelTimer tm(K_SELSCAN_FWD, st);
-#define GFE_FWD_FAST(HZ, CPB, PP)                                                                              \
-    launch_fast(selscan_fwd_fast_kernel<T, HZ, CPB, PP>, gridf, block, (size_t)W * fwd_fast_smem_per_warp<T, HZ, PP>(), st, p)
-        if (P == 2) {
-            if (hz && cpb == 16) GFE_FWD_FAST(true, 16, 2);
-            else if (hz) GFE_FWD_FAST(true, 4, 2);
-            else if (cpb == 16) GFE_FWD_FAST(false, 16, 2);
-            else GFE_FWD_FAST(false, 4, 2);
-        } else {
-            if (hz && cpb == 16) GFE_FWD_FAST(true, 16, 1);
-            else if (hz) GFE_FWD_FAST(true, 4, 1);
-            else if (cpb == 16) GFE_FWD_FAST(false, 16, 1);
-            else GFE_FWD_FAST(false, 4, 1);
-        }
-#undef GFE_FWD_FAST
-    } else {
+    {
         const size_t smem = (size_t)W * 2 * kChunk * 32 * sizeof(float);
         ScopedKernelTimer tm(K_SELSCAN_FWD, st);
         if (a->z != nullptr) selscan_fwd_kernel<T, true><<<grid, block, smem, st>>>(p);
@@ -793,22 +740,7 @@ static int launch_bwd_z(const gfe_selscan_args *a, ScanParams &p, const SegPlan 
         if (rc != GFE_OK) return rc;
     }
     const dim3 grid((p.G + W - 1) / W, sp.nseg, a->batch);
-    const int cpb = fast_path_cpb(a, true);
-    if (cpb != 0) {
-        const int P = sp.p_bwd;
-        p.G = a->d_inner / (32 / P);
-        const dim3 gridf((p.G + W - 1) / W, sp.nseg, a->batch);
-        ScopedKernelTimer tm(K_SELSCAN_BWD, st);
-        if (P == 2) {
-            const size_t smem = (size_t)W * bwd_fast_smem_per_warp<T, HAS_Z, 2>();
-            if (cpb == 16) launch_fast(selscan_bwd_fast_kernel<T, HAS_Z, 16, 2>, gridf, block, smem, st, p);
-            else launch_fast(selscan_bwd_fast_kernel<T, HAS_Z, 4, 2>, gridf, block, smem, st, p);
-        } else {
-            const size_t smem = (size_t)W * bwd_fast_smem_per_warp<T, HAS_Z, 1>();
-            if (cpb == 16) launch_fast(selscan_bwd_fast_kernel<T, HAS_Z, 16, 1>, gridf, block, smem, st, p);
-            else launch_fast(selscan_bwd_fast_kernel<T, HAS_Z, 4, 1>, gridf, block, smem, st, p);
-        }
-    } else {
+    {
         const size_t smem = (size_t)W * kBwdSmemFloats * sizeof(float);
         ScopedKernelTimer tm(K_SELSCAN_BWD, st);
         launch_fast(selscan_bwd_kernel<T, HAS_Z>, grid, block, smem, st, p);

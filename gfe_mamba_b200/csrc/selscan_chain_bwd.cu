@@ -25,9 +25,9 @@
 
 namespace gfe {
 
-void chain_bwd_plan(int B, int L, int ED, int &cpc, int &nblk, int &nseg, int &seg_len);
-int chain_fill_sched(ChainSched &cs, char *ws, int B, int ED, int nblk, int nseg, int seg_len, cudaStream_t st);
-size_t chain_bytes(int B, int ED, int nblk, int nseg);
+int chain_fill_sched(ChainSched &cs, char *ws, int B, int ED, const ChainPlan &pl, cudaStream_t st);
+size_t chain_bytes(int B, int ED, const ChainPlan &pl);
+int seg_launch_carries(const ScanParams &p, const ChainSched &cs, int dtype, int cpc, bool rev, bool has_z, int cpb, cudaStream_t st);   // selscan_seg.cu
 void chain_fill_params(ScanParams &p, const gfe_selscan_args *a);
 int chain_cpb(const gfe_selscan_args *a, bool bwd);
 bool chain_pair_stores(const gfe_selscan_args *a, bool bwd);
@@ -232,13 +232,16 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
         const float2 Dc = __ldg(reinterpret_cast<const float2 *>(p.D + c0) + cp);                                                // phase C pair
         float2 dD_acc = make_float2(0.f, 0.f), dbias_acc = make_float2(0.f, 0.f);
 
-        float *carry = cs.carry + ((size_t)b * p.ED + c0 + 2 * rp) * kNState + 4 * rq;
+        float *carry = cs.independent ? cs.segc + (((size_t)(rseg > 0 ? seg : 0) * p.B + b) * p.ED + c0 + 2 * rp) * kNState + 4 * rq
+                                      : cs.carry + ((size_t)b * p.ED + c0 + 2 * rp) * kNState + 4 * rq;
         if (rseg > 0) {
-            if (tid == 0) {
-                const int *f = cs.flags + (unit - per_seg);
-                while (ld_acquire(f) == 0) __nanosleep(100);
+            if (!cs.independent) {
+                if (tid == 0) {
+                    const int *f = cs.flags + (unit - per_seg);
+                    while (ld_acquire(f) == 0) __nanosleep(100);
+                }
+                __syncthreads();
             }
-            __syncthreads();
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
                 const float4 v = __ldcg(reinterpret_cast<const float4 *>(carry + ch * kNState));
@@ -520,7 +523,7 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
             *reinterpret_cast<float2 *>(dst + (size_t)16 * p.ED) = dD_acc;
             *reinterpret_cast<float2 *>(dst + (size_t)17 * p.ED) = dbias_acc;
         }
-        if (seg > 0) {
+        if (seg > 0 && !cs.independent) {
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
                 const float4 gv = sw ? make_float4(G[ch][0].y, G[ch][0].x, G[ch][1].y, G[ch][1].x)
@@ -553,14 +556,13 @@ struct BwdWs {
     size_t part_bc, part_par, total;
 };
 static BwdWs bwd_ws(int B, int L, int ED) {
-    int cpc, nblk, nseg, seg_len;
-    chain_bwd_plan(B, L, ED, cpc, nblk, nseg, seg_len);
+    const ChainPlan pl = chain_bwd_plan(B, L, ED);
     BwdWs w{};
-    size_t off = chain_bytes(B, ED, nblk, nseg);
+    size_t off = chain_bytes(B, ED, pl);
     w.part_bc = off;
-    off += align_up((size_t)nblk * B * L * 32 * sizeof(float), 256);
+    off += align_up((size_t)pl.nblk * B * L * 32 * sizeof(float), 256);
     w.part_par = off;
-    off += align_up((size_t)B * nseg * 18 * ED * sizeof(float), 256);
+    off += align_up((size_t)B * pl.nseg * 18 * ED * sizeof(float), 256);
     w.total = off;
     return w;
 }
@@ -587,8 +589,8 @@ static void launch_bwd_chain_cpc(const ScanParams &p, const ChainSched &cs, bool
 
 template <typename T>
 static int launch_bwd_chain_t(const gfe_selscan_args *a, cudaStream_t st) {
-    int cpc, nblk, nseg, seg_len;
-    chain_bwd_plan(a->batch, a->seqlen, a->d_inner, cpc, nblk, nseg, seg_len);
+    const ChainPlan pl = chain_bwd_plan(a->batch, a->seqlen, a->d_inner);
+    const int cpc = pl.cpc, nblk = pl.nblk, nseg = pl.nseg;
     const BwdWs w = bwd_ws(a->batch, a->seqlen, a->d_inner);
     if (a->ws == nullptr || a->ws_bytes < w.total) {
         set_error("selscan_bwd: workspace too small (%zu < %zu)", a->ws ? a->ws_bytes : (size_t)0, w.total);
@@ -612,10 +614,15 @@ static int launch_bwd_chain_t(const gfe_selscan_args *a, cudaStream_t st) {
     p.G = nblk;      // finalize_bc sums one row per channel block
     p.bc_interleaved = 1;
     ChainSched cs{};
-    rc = chain_fill_sched(cs, ws, a->batch, a->d_inner, nblk, nseg, seg_len, st);
+    rc = chain_fill_sched(cs, ws, a->batch, a->d_inner, pl, st);
     if (rc != GFE_OK) return rc;
     const int cpb = chain_cpb(a, true);
     if (chain_pair_stores(a, true)) p.flags |= kFlagPairStores;
+    if (pl.independent && nseg > 1) {
+        ScopedKernelTimer tm(K_SELSCAN_BWD_SUMMARY, st);
+        rc = seg_launch_carries(p, cs, a->dtype, cpc, true, a->z != nullptr, cpb, st);
+        if (rc != GFE_OK) return rc;
+    }
     {
         ScopedKernelTimer tm(K_SELSCAN_BWD, st);
         const bool hz = a->z != nullptr;

@@ -13,12 +13,15 @@ namespace gfe {
 template <typename T>
 void v4_launch_fwd_kernel(const ScanParams &p, const ChainSched &cs, int cpc, bool has_z, int cpb, cudaStream_t st);   // selscan_v4_fwd.cu
 
+int seg_launch_carries(const ScanParams &p, const ChainSched &cs, int dtype, int cpc, bool rev, bool has_z, int cpb, cudaStream_t st);   // selscan_seg.cu
+
 // L is cut into chained segments, ~12 units per resident CTA: the units of a chain interleave with those of the others and
 // hop between SMs, which evens out SMs that host 2 and 3 working CTAs (measured on cfg3, profiles/r02_chain_variants.txt:
-// 10-16 segments beat 1, 4 and 32 by 2-4 %).
-static void chain_plan(int B, int L, int nblk, int ctas_per_sm, int &nseg, int &seg_len) {
+// 10-16 segments beat 1, 4 and 32 by 2-4 %).  Independent segments (too few chains to fill the GPU) only need enough units
+// for the dynamic scheduler to balance the resident CTAs: ~3 per CTA.
+static void chain_plan(int B, int L, int nblk, int ctas_per_sm, bool independent, int &nseg, int &seg_len) {
     const int64_t slots = (int64_t)sm_count() * ctas_per_sm;
-    int64_t want = ceil_div64(12 * slots, (int64_t)B * nblk);
+    int64_t want = ceil_div64((independent ? GFE_SEG_UNITS_PER_CTA : 12) * slots, (int64_t)B * nblk);
 #ifdef GFE_EXPERIMENTS
     if (const char *e = getenv("GFE_CHAIN_NSEG")) want = atoi(e);   // A/B measurements only
 #endif
@@ -51,63 +54,75 @@ static int bwd_cpc(int ED) {
     return ED % GFE_BWD_CPC_DEFAULT == 0 ? GFE_BWD_CPC_DEFAULT : 32;
 }
 
-void chain_fwd_plan(int B, int L, int ED, int &cpc, int &nblk, int &nseg, int &seg_len) {
-    cpc = fwd_cpc(ED);
-    nblk = ED / cpc;
-    chain_plan(B, L, nblk, 3 * (64 / cpc), nseg, seg_len);
-}
-void chain_bwd_plan(int B, int L, int ED, int &cpc, int &nblk, int &nseg, int &seg_len) {
-    cpc = bwd_cpc(ED);
-    nblk = ED / cpc;
-    chain_plan(B, L, nblk, GFE_CBWD_MINB * (64 / cpc), nseg, seg_len);
-}
-
-// The chained kernels serve every shape with ED % 32 == 0 that offers enough (row, channel) parallelism to fill the GPU
-// without splitting L; smaller problems take the L-split pair (selscan.cu), which recomputes instead of waiting.
-bool chain_applicable(int B, int L, int ED) {
-    if (ED % 32 != 0) return false;
+// Chains wait for their predecessor segment when B * ED alone fills the GPU (plan_segments: at least half the schedulers
+// get a warp without splitting L); otherwise the segments are made independent by a summary + combine pass.
+static bool chain_independent(int B, int L, int ED) {
 #ifdef GFE_EXPERIMENTS
-    if (const char *e = getenv("GFE_SELSCAN_CHAIN")) {   // A/B measurements only
-        if (e[0] == '0') return false;
-        if (e[0] == '1') return true;
+    if (const char *e = getenv("GFE_SELSCAN_CHAIN")) {   // A/B measurements only: 1 = always wait, 2 = always independent
+        if (e[0] == '1') return false;
+        if (e[0] == '2') return true;
     }
 #endif
-    return plan_segments(B, L, ED).nseg == 1;
+    return plan_segments(B, L, ED).nseg > 1;
+}
+
+ChainPlan chain_fwd_plan(int B, int L, int ED) {
+    ChainPlan pl{};
+    pl.cpc = fwd_cpc(ED);
+    pl.nblk = ED / pl.cpc;
+    pl.independent = chain_independent(B, L, ED) ? 1 : 0;
+    chain_plan(B, L, pl.nblk, 3 * (64 / pl.cpc), pl.independent, pl.nseg, pl.seg_len);
+    return pl;
+}
+ChainPlan chain_bwd_plan(int B, int L, int ED) {
+    ChainPlan pl{};
+    pl.cpc = bwd_cpc(ED);
+    pl.nblk = ED / pl.cpc;
+    pl.independent = chain_independent(B, L, ED) ? 1 : 0;
+    chain_plan(B, L, pl.nblk, GFE_CBWD_MINB * (64 / pl.cpc), pl.independent, pl.nseg, pl.seg_len);
+    return pl;
+}
+
+// The chained kernels serve every shape with ED % 32 == 0 (other widths take the generic kernels in selscan.cu).
+bool chain_applicable(int B, int L, int ED) {
+    (void)B; (void)L;
+    return ED % 32 == 0;
 }
 
 struct ChainLayout {
-    size_t counter, flags, carry, total;
+    size_t counter, flags, carry, segsd, total;
 };
-static ChainLayout chain_layout(int B, int ED, int nblk, int nseg) {
+static ChainLayout chain_layout(int B, int ED, const ChainPlan &pl) {
     ChainLayout c{};
     size_t off = 0;
-    c.counter = off;
+    c.counter = off;   // [0]: main pass, [16]: summary pass
     off += 256;
     c.flags = off;
-    off += align_up((size_t)nseg * B * nblk * sizeof(int), 256);
-    c.carry = off;
-    off += align_up((size_t)B * ED * kNState * sizeof(float), 256);
+    off += align_up(pl.independent ? 0 : (size_t)pl.nseg * B * pl.nblk * sizeof(int), 256);
+    c.carry = off;     // chained: [B][ED][16]; independent: [nseg - 1][B][ED][16] followed by sum(delta) [nseg - 1][B][ED]
+    off += align_up((size_t)(pl.independent ? pl.nseg - 1 : 1) * B * ED * kNState * sizeof(float), 256);
+    c.segsd = off;
+    off += align_up(pl.independent ? (size_t)(pl.nseg - 1) * B * ED * sizeof(float) : 0, 256);
     c.total = off;
     return c;
 }
 
-size_t chain_bytes(int B, int ED, int nblk, int nseg) { return chain_layout(B, ED, nblk, nseg).total; }
+size_t chain_bytes(int B, int ED, const ChainPlan &pl) { return chain_layout(B, ED, pl).total; }
 
-size_t chain_fwd_workspace_bytes(int B, int L, int ED) {
-    int cpc, nblk, nseg, seg_len;
-    chain_fwd_plan(B, L, ED, cpc, nblk, nseg, seg_len);
-    return chain_layout(B, ED, nblk, nseg).total;
-}
+size_t chain_fwd_workspace_bytes(int B, int L, int ED) { return chain_layout(B, ED, chain_fwd_plan(B, L, ED)).total; }
 
-int chain_fill_sched(ChainSched &cs, char *ws, int B, int ED, int nblk, int nseg, int seg_len, cudaStream_t st) {
-    const ChainLayout cl = chain_layout(B, ED, nblk, nseg);
+int chain_fill_sched(ChainSched &cs, char *ws, int B, int ED, const ChainPlan &pl, cudaStream_t st) {
+    const ChainLayout cl = chain_layout(B, ED, pl);
     cs.counter = reinterpret_cast<int *>(ws + cl.counter);
     cs.flags = reinterpret_cast<int *>(ws + cl.flags);
     cs.carry = reinterpret_cast<float *>(ws + cl.carry);
-    cs.nseg = nseg;
-    cs.seg_len = seg_len;
-    cs.nblk = nblk;
-    cs.total = nseg * B * nblk;
+    cs.nseg = pl.nseg;
+    cs.seg_len = pl.seg_len;
+    cs.nblk = pl.nblk;
+    cs.total = pl.nseg * B * pl.nblk;
+    cs.independent = pl.independent;
+    cs.segc = cs.carry;
+    cs.segsd = reinterpret_cast<float *>(ws + cl.segsd);
     if (cudaMemsetAsync(ws, 0, cl.carry, st) != cudaSuccess) return check_launch("selscan chain memset");
     return GFE_OK;
 }
@@ -185,9 +200,8 @@ bool chain_pair_stores(const gfe_selscan_args *a, bool bwd) {
 
 template <typename T>
 static int launch_fwd_chain_t(const gfe_selscan_args *a, cudaStream_t st) {
-    int cpc, nblk, nseg, seg_len;
-    chain_fwd_plan(a->batch, a->seqlen, a->d_inner, cpc, nblk, nseg, seg_len);
-    const size_t need = chain_bytes(a->batch, a->d_inner, nblk, nseg);
+    const ChainPlan pl = chain_fwd_plan(a->batch, a->seqlen, a->d_inner);
+    const size_t need = chain_bytes(a->batch, a->d_inner, pl);
     if (a->ws == nullptr || a->ws_bytes < need) {
         set_error("selscan_fwd: workspace too small (%zu < %zu)", a->ws ? a->ws_bytes : (size_t)0, need);
         return GFE_ERR_WORKSPACE;
@@ -198,12 +212,18 @@ static int launch_fwd_chain_t(const gfe_selscan_args *a, cudaStream_t st) {
     chain_fill_params(p, a);
     p.out = a->out; p.o_bs = a->out_bs; p.o_rs = a->out_rs; p.last_state = a->last_state;
     ChainSched cs{};
-    rc = chain_fill_sched(cs, reinterpret_cast<char *>(a->ws), a->batch, a->d_inner, nblk, nseg, seg_len, st);
+    rc = chain_fill_sched(cs, reinterpret_cast<char *>(a->ws), a->batch, a->d_inner, pl, st);
     if (rc != GFE_OK) return rc;
     if (chain_pair_stores(a, false)) p.flags |= kFlagPairStores;
+    const int cpb = chain_cpb(a, false);
+    if (pl.independent && pl.nseg > 1) {
+        ScopedKernelTimer tm(K_SELSCAN_FWD_SUMMARY, st);
+        rc = seg_launch_carries(p, cs, a->dtype, pl.cpc, false, false, cpb, st);
+        if (rc != GFE_OK) return rc;
+    }
     {
         ScopedKernelTimer tm(K_SELSCAN_FWD, st);
-        v4_launch_fwd_kernel<T>(p, cs, cpc, a->z != nullptr, chain_cpb(a, false), st);
+        v4_launch_fwd_kernel<T>(p, cs, pl.cpc, a->z != nullptr, cpb, st);
     }
     return check_launch("selscan_fwd (chained)");
 }

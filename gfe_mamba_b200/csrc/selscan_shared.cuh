@@ -49,6 +49,12 @@ struct ChainSched {
     int *flags;     // [nseg][B * nblk], zeroed before the launch
     float *carry;   // [B][ED][16] state handed from one segment to the next
     int nseg, seg_len, nblk, total;
+    // Independent segments (small B * ED: too few chains to fill the GPU by waiting): every segment's carry-in is known
+    // before the launch -- a summary pass (selscan_seg.cu) leaves each segment's local aggregate and sum(delta), a combine
+    // pass turns them into carries -- so units neither wait nor publish.
+    int independent;
+    float *segc;    // [nseg - 1][B][ED][16]  slot s: forward carry-in of segment s + 1 / reverse carry-in of segment s
+    float *segsd;   // [nseg - 1][B][ED]      sum of delta over the segment the slot's aggregate was taken from
 };
 
 #ifdef __CUDACC__
@@ -320,6 +326,16 @@ static int persistent_grid(int nt, size_t smem, int total) {
 #ifndef GFE_CBWD_MINB
 #define GFE_CBWD_MINB 2        // backward: CTAs of 128 threads per SM the register budget is set for (2: 255 registers, 3: 168)
 #endif
+#ifndef GFE_SEG_UNITS_PER_CTA
+#define GFE_SEG_UNITS_PER_CTA 3   // independent segments: units per resident CTA the plan aims for
+#endif
+struct ChainPlan {
+    int cpc, nblk;          // channel-block width and count
+    int nseg, seg_len;      // L-segments (seg_len a multiple of kChunk)
+    int independent;        // 0: segments wait for their predecessor; 1: carries come from the summary + combine passes
+};
+ChainPlan chain_fwd_plan(int B, int L, int ED);
+ChainPlan chain_bwd_plan(int B, int L, int ED);
 bool chain_applicable(int B, int L, int ED);              // shape-only: both directions take the same decision
 size_t chain_ckpt_state_bytes(int B, int L, int ED, int dtype);
 size_t chain_fwd_workspace_bytes(int B, int L, int ED);

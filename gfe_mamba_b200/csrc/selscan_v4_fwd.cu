@@ -226,13 +226,16 @@ __global__ void __launch_bounds__(2 * CPC, GFE_V4_MINB * (64 / CPC)) selscan_fwd
         const float2 bias = p.dt_bias ? __ldg(reinterpret_cast<const float2 *>(p.dt_bias + c0) + ip) : make_float2(0.f, 0.f);
 
         // carry-in: the state our predecessor segment left behind
-        float *carry = cs.carry + ((size_t)b * p.ED + c0 + 2 * rp) * kNState + 4 * rq;
+        float *carry = cs.independent ? cs.segc + (((size_t)(seg > 0 ? seg - 1 : 0) * p.B + b) * p.ED + c0 + 2 * rp) * kNState + 4 * rq
+                                      : cs.carry + ((size_t)b * p.ED + c0 + 2 * rp) * kNState + 4 * rq;
         if (seg > 0) {
-            if (tid == 0) {
-                const int *f = cs.flags + (unit - per_seg);
-                while (ld_acquire(f) == 0) __nanosleep(100);
+            if (!cs.independent) {
+                if (tid == 0) {
+                    const int *f = cs.flags + (unit - per_seg);
+                    while (ld_acquire(f) == 0) __nanosleep(100);
+                }
+                __syncthreads();
             }
-            __syncthreads();
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
                 const float4 v = __ldcg(reinterpret_cast<const float4 *>(carry + ch * kNState));
@@ -349,7 +352,7 @@ __global__ void __launch_bounds__(2 * CPC, GFE_V4_MINB * (64 / CPC)) selscan_fwd
                     *(reinterpret_cast<float4 *>(p.last_state + ((size_t)b * p.ED + c0 + 2 * rp + ch) * kNState) + rq) =
                         make_float4(h[ch][0].x, h[ch][0].y, h[ch][1].x, h[ch][1].y);
             }
-        } else {
+        } else if (!cs.independent) {
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch)
                 __stcg(reinterpret_cast<float4 *>(carry + ch * kNState), make_float4(h[ch][0].x, h[ch][0].y, h[ch][1].x, h[ch][1].y));

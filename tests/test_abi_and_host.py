@@ -44,7 +44,8 @@ def test_size_queries_without_gpu():
     B, L, ED, N = 16, 4096, 1536, 16
     states = B * (L // 8) * ED * N * 4                              # chained kernels checkpoint every 8 steps
     assert lib.gfe_selscan_ckpt_bytes(B, L, ED, N) == states + B * L * ED * 4
-    assert lib.gfe_selscan_ckpt_bytes(1, 65536, 1024, N) == (65536 // 16) * 1024 * N * 4 + 65536 * 1024 * 4   # L-split path: 16
+    assert lib.gfe_selscan_ckpt_bytes(1, 65536, 1024, N) == (65536 // 8) * 1024 * N * 4 + 65536 * 1024 * 4   # independent segments: same layout
+    assert lib.gfe_selscan_ckpt_bytes(1, 65536, 1000, N) == (65536 // 16) * 1000 * N * 4 + 65536 * 1000 * 4  # generic kernels (ED % 32 != 0): every 16
     assert lib.gfe_selscan_ckpt_bytes(B, L, ED, 8) == 0            # unsupported d_state -> 0
     # bf16 activations: bf16 state checkpoints and y before the gate in bf16 -- half of everything saved for backward
     assert lib.gfe_selscan_ckpt_bytes_dt(B, L, ED, N, _native.GFE_BF16) == states // 2 + B * L * ED * 2 <= 0.61e9

@@ -216,6 +216,41 @@ def test_selscan_l_split_path():
     compare(run_fused(d, torch.float32), oracle_fused(d, torch.float32), TOL[torch.float32])
 
 
+@pytest.mark.parametrize("use_z,use_bias,softplus,dtype", [(True, True, True, torch.float32), (False, True, True, torch.float32),
+                                                           (True, False, False, torch.float32), (True, True, True, torch.bfloat16),
+                                                           (False, False, True, torch.float16)])
+def test_selscan_independent_segments_variants(use_z, use_bias, softplus, dtype):
+    """Independent L-segments (summary + combine + main pass on the chained kernels): 32-channel blocks (ED % 64 == 32), ragged
+    last segment, every flag combination of the reverse summary (dy = dout silu(z) | dout)."""
+    d = make_scan_inputs(1, 2100, 96, seed=7)
+    if not softplus:
+        d["draw"] = np.abs(d["draw"]) * 0.2 + 1e-3
+        d["bias"] = np.abs(d["bias"]) * 0.01
+    compare(run_fused(d, dtype, use_z, use_bias, softplus), oracle_fused(d, dtype, use_z, use_bias, softplus), TOL[dtype])
+
+
+def test_selscan_independent_segments_unaligned_views():
+    """The same path on views that rule out 16-byte cp.async pieces (B/C slices at a 4-element offset of a wider tensor)."""
+    from gfe_mamba_b200 import selective_scan_fn
+    B, L, ED, N, R = 1, 1500, 64, 16, 4
+    d = make_scan_inputs(B, L, ED, seed=23)
+    xz = cuda(np.concatenate([d["u"], d["z"]], -1), grad=True)
+    dbc = cuda(np.concatenate([np.zeros((B, L, R + 1), np.float32), d["Bm"], d["Cm"]], -1), grad=True)
+    u, z = xz.chunk(2, dim=-1)
+    _, Bm, Cm = torch.split(dbc, [R + 1, N, N], dim=-1)
+    draw = cuda(d["draw"], grad=True)
+    A_log, D, bias = cuda(d["A_log"], grad=True), cuda(d["D"], grad=True), cuda(d["bias"], grad=True)
+    out = selective_scan_fn(u, draw, A_log, Bm, Cm, D, z=z, dt_bias=bias)
+    out.backward(cuda(d["dout"]))
+    want = oracle_fused(d, torch.float32)
+    tol = TOL[torch.float32]
+    assert relerr(out, want["out"]) < tol
+    assert relerr(xz.grad[..., :ED], want["du"]) < tol and relerr(xz.grad[..., ED:], want["dz"]) < tol
+    assert relerr(draw.grad, want["ddelta"]) < tol
+    assert relerr(dbc.grad[..., R + 1:R + 1 + N], want["dB"]) < tol and relerr(dbc.grad[..., R + 1 + N:], want["dC"]) < tol
+    assert relerr(A_log.grad, want["dA_log"]) < tol and relerr(bias.grad, want["ddt_bias"]) < tol
+
+
 def test_selscan_strided_views():
     """u/z as the halves of one (B, L, 2ED) tensor, B/C as slices of (B, L, R+2N): consumed in place."""
     from gfe_mamba_b200 import selective_scan_fn
