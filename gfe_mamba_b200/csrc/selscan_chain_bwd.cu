@@ -20,6 +20,8 @@
 //   phase C  (warp-local item mapping, right after each half: only __syncwarp): du, ddelta from the four quads'
 //            partials; dD / ddt_bias accumulation;
 //   then the warps' dB|dC rows are added and leave as one row per (CTA, t) for selscan_bwd_finalize_bc.
+#include <type_traits>
+
 #include "common.cuh"
 #include "selscan_shared.cuh"
 
@@ -97,7 +99,7 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
     float4 *sS = reinterpret_cast<float4 *>(smem + SM::kOffS);
     float *sRed = reinterpret_cast<float *>(smem + SM::kOffRed);
     const bool sp = p.flags & GFE_FLAG_DELTA_SOFTPLUS;
-    const bool vec = p.flags & kFlagPairStores;
+    constexpr bool vec = CPB == 16;   // the cp.async instantiation also requires pair-aligned outputs (chain_launch_bwd)
     const int per_seg = p.B * cs.nblk;
 
     // recurrence-side shared pointers (fixed for the whole kernel)
@@ -142,29 +144,34 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
         T *ddb = reinterpret_cast<T *>(p.ddelta) + (int64_t)b * p.dd_bs + c0 + 2 * cp;
         T *dzb = HAS_Z ? reinterpret_cast<T *>(p.dz) + (int64_t)b * p.dz_bs + c0 + 2 * ip : nullptr;
 
-        // per-thread source pointers of the staged pieces at row 0 of this batch row (cp.async path)
-        const char *su = nullptr, *sd = nullptr, *sg_ = nullptr, *sy = nullptr, *sz = nullptr, *sbc[BCI];
-        int64_t rs_bc[BCI];
+        // per-thread source pointers of the staged pieces of the NEXT chunk to issue (cp.async path): chunks are issued strictly in
+        // processing order (klast, klast - 1, ...), so every pointer just steps back by one chunk after each issue
+        const char *su = nullptr, *sd = nullptr, *sg_ = nullptr, *sy = nullptr, *sz = nullptr, *sbc[BCI], *sck = nullptr;
         int bcrow[BCI];
+        constexpr int PH = SM::kCk / 16;      // 16-byte pieces per half-chunk checkpoint block: NT (16-bit states) or 2 NT (fp32)
+        static_assert(PH % NT == 0 && CKP == 2 * (PH / NT), "checkpoint staging layout");
+        sck = ckb + (size_t)(2 * klast) * ck_step + tid * 16;
         if constexpr (CPB == 16) {
-            su = reinterpret_cast<const char *>(ub + (int64_t)srow * p.u_rs) + spiece * 16;
-            sd = reinterpret_cast<const char *>(db + (int64_t)srow * p.d_rs) + spiece * 16;
-            sg_ = reinterpret_cast<const char *>(gb + (int64_t)srow * p.do_rs) + spiece * 16;
+            const int64_t r0 = (int64_t)klast * kChunk + srow;
+            su = reinterpret_cast<const char *>(ub + r0 * p.u_rs) + spiece * 16;
+            sd = reinterpret_cast<const char *>(db + r0 * p.d_rs) + spiece * 16;
+            sg_ = reinterpret_cast<const char *>(gb + r0 * p.do_rs) + spiece * 16;
             if (HAS_Z) {
-                sy = reinterpret_cast<const char *>(yb + (int64_t)srow * p.ED) + spiece * 16;
-                sz = reinterpret_cast<const char *>(zb + (int64_t)srow * p.z_rs) + spiece * 16;
+                sy = reinterpret_cast<const char *>(yb + r0 * p.ED) + spiece * 16;
+                sz = reinterpret_cast<const char *>(zb + r0 * p.z_rs) + spiece * 16;
             }
 #pragma unroll
             for (int i = 0; i < BCI; ++i) {
                 const int pc = tid + i * NT;
                 const int sel = pc / BCP, within = pc % BCP;    // 0: B, 1: C
                 bcrow[i] = within / (BCP / kChunk);
-                rs_bc[i] = (sel ? p.C_rs : p.B_rs) * (int64_t)sizeof(T);
-                sbc[i] = reinterpret_cast<const char *>((sel ? Cb : Bb)) + bcrow[i] * rs_bc[i] + (within % (BCP / kChunk)) * 16;
+                const int64_t rs = sel ? p.C_rs : p.B_rs;
+                sbc[i] = reinterpret_cast<const char *>((sel ? Cb : Bb) + ((int64_t)klast * kChunk + bcrow[i]) * rs) + (within % (BCP / kChunk)) * 16;
             }
         }
         const uint32_t dst_act = smem_u32(smem) + srow * RB + spiece * 16;
         const uint32_t dst_bc = smem_u32(smem) + NTILE * SM::kTile + tid * 16;   // raw B tile followed by raw C tile
+        const uint32_t dst_ck = smem_u32(smem) + SM::kOffCk + tid * 16;
 
         auto issue = [&](int i, int stage) {   // i-th chunk in processing order (global chunk klast - i) -> stage i % NST
             if (i < nch) {
@@ -174,31 +181,33 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
                 {   // both halves' checkpoints (states before steps tb and tb + 8); always 16-byte aligned
                     const int nhalf = tb + kCkptV2 < t1 ? 2 : 1;
 #pragma unroll
-                    for (int q = 0; q < CKP; ++q) {
-                        const int pc = tid + q * NT;                        // piece of [half][c][16]
-                        const int half = pc / (SM::kCk / 16), within = pc % (SM::kCk / 16);
-                        if (half < nhalf)
-                            cp_async<16>(smem_u32(smem) + so + SM::kOffCk + pc * 16,
-                                         ckb + (size_t)(2 * (klast - i) + half) * ck_step + within * 16);
+                    for (int q = 0; q < CKP; ++q) {   // piece tid + q NT of [half][c][16]
+                        constexpr int QH = PH / NT;    // pieces per thread and half
+                        if (q / QH < nhalf) cp_async<16>(dst_ck + so + q * NT * 16, sck + (size_t)(q / QH) * ck_step + (q % QH) * NT * 16);
                     }
+                    sck -= 2 * ck_step;
                 }
                 if constexpr (CPB == 16) {
                     if (srow < nrows) {
-                        const int64_t sz_t = (int64_t)sizeof(T);
 #pragma unroll
                         for (int q = 0; q < PPT; ++q) {
-                            cp_async<16>(dst_act + so + q * 16, su + (int64_t)tb * p.u_rs * sz_t + q * 16);
-                            cp_async<16>(dst_act + so + SM::kTile + q * 16, sd + (int64_t)tb * p.d_rs * sz_t + q * 16);
-                            cp_async<16>(dst_act + so + 2 * SM::kTile + q * 16, sg_ + (int64_t)tb * p.do_rs * sz_t + q * 16);
+                            cp_async<16>(dst_act + so + q * 16, su + q * 16);
+                            cp_async<16>(dst_act + so + SM::kTile + q * 16, sd + q * 16);
+                            cp_async<16>(dst_act + so + 2 * SM::kTile + q * 16, sg_ + q * 16);
                             if (HAS_Z) {
-                                cp_async<16>(dst_act + so + 3 * SM::kTile + q * 16, sy + (int64_t)tb * p.ED * sz_t + q * 16);
-                                cp_async<16>(dst_act + so + 4 * SM::kTile + q * 16, sz + (int64_t)tb * p.z_rs * sz_t + q * 16);
+                                cp_async<16>(dst_act + so + 3 * SM::kTile + q * 16, sy + q * 16);
+                                cp_async<16>(dst_act + so + 4 * SM::kTile + q * 16, sz + q * 16);
                             }
                         }
                     }
 #pragma unroll
                     for (int q = 0; q < BCI; ++q)
-                        if (tid + q * NT < 2 * BCP && bcrow[q] < nrows) cp_async<16>(dst_bc + so + q * NT * 16, sbc[q] + (int64_t)tb * rs_bc[q]);
+                        if (tid + q * NT < 2 * BCP && bcrow[q] < nrows) cp_async<16>(dst_bc + so + q * NT * 16, sbc[q]);
+                    constexpr int64_t sz_t = (int64_t)sizeof(T) * kChunk;
+                    su -= p.u_rs * sz_t; sd -= p.d_rs * sz_t; sg_ -= p.do_rs * sz_t;
+                    if (HAS_Z) { sy -= (int64_t)p.ED * sz_t; sz -= p.z_rs * sz_t; }
+#pragma unroll
+                    for (int q = 0; q < BCI; ++q) sbc[q] -= ((tid + q * NT) / BCP ? p.C_rs : p.B_rs) * sz_t;
                 } else {
                     unsigned char *s = smem + so;
                     stage_tile<T, 0, CPC, NT>(s, ub + (int64_t)tb * p.u_rs, p.u_rs, nrows, tid);
@@ -253,7 +262,10 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
             for (int ch = 0; ch < 2; ++ch) G[ch][0] = G[ch][1] = make_float2(0.f, 0.f);
         }
 
-        auto phase_a = [&](int i, int stage) {
+        // FULL: all 16 rows of the chunk lie inside the sequence (every chunk but a ragged last one): no row masking at all.
+        // Slot layouts follow the packed register pairs: {dl0, dl1, dl0 u0, dl1 u1}, {dy0, dy1}, {u0, u1, softplus'0, softplus'1}.
+        auto phase_a = [&](int i, int stage, auto full_c) {
+            constexpr bool FULL = decltype(full_c)::value;
             const int tb = (klast - i) * kChunk;
             const unsigned char *s = smem + stage * SM::kStage;
             const T *sU = reinterpret_cast<const T *>(s);
@@ -265,12 +277,12 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
             float2 dl[4], sg[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {   // branch-free packed softplus + sigmoid (selscan_shared.cuh)
-                const float2 d2 = lds_pair(sD + (ir + 4 * q) * CPC, ip);
-                const float2 x = make_float2(d2.x + bias.x, d2.y + bias.y);
-                float2 sg2;
-                const float2 v = softplus_pair<true>(x, sg2);
-                dl[q] = sp ? v : x;
-                sg[q] = sp ? sg2 : make_float2(1.0f, 1.0f);
+                dl[q] = fadd2(lds_pair(sD + (ir + 4 * q) * CPC, ip), bias);
+                sg[q] = make_float2(1.0f, 1.0f);
+            }
+            if (sp) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) dl[q] = softplus_pair<true>(dl[q], sg[q]);
             }
             float2 uq[4], gq[4], zq[4], yq[4];   // every load of the phase before its first store (an LDS is never moved above an STS)
 #pragma unroll
@@ -288,33 +300,35 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
             for (int q = 0; q < BCC; ++q) {
                 const int e = tid + q * NT, t = e >> 3, q8 = e & 7;
                 bcv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (tb + t < t1) {
-                    const T *src = sBr + (q8 < 4 ? 0 : kChunk * 16) + t * 16 + 4 * (q8 & 3);
-                    const float2 lo = lds_pair(src, 0), hi = lds_pair(src, 1);
-                    bcv[q] = make_float4(lo.x, lo.y, hi.x, hi.y);
-                }
+                if (FULL || tb + t < t1) bcv[q] = lds_quad(sBr + (q8 < 4 ? 0 : kChunk * 16) + t * 16 + 4 * (q8 & 3));
             }
+            T *dzp = HAS_Z ? dzb + ((int64_t)tb + ir) * p.dz_rs : nullptr;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int t = ir + 4 * q;
-                const bool valid = tb + t < t1;
-                const float u0 = valid ? uq[q].x : 0.f, u1 = valid ? uq[q].y : 0.f;
-                const float do0 = valid ? gq[q].x : 0.f, do1 = valid ? gq[q].y : 0.f;
-                const float dl0 = valid ? dl[q].x : 0.f, dl1 = valid ? dl[q].y : 0.f;   // padded step: a = 1, bx = 0, dy = 0
-                float dy0 = do0, dy1 = do1;
+                const bool valid = FULL || tb + t < t1;
+                float2 u2 = uq[q], do2 = gq[q], dl2 = dl[q];
+                if (!FULL && !valid) u2 = do2 = dl2 = make_float2(0.f, 0.f);   // padded step: a = 1, bx = 0, dy = 0
+                float2 dy2 = do2;
                 if (HAS_Z) {
-                    const float z0 = valid ? zq[q].x : 0.f, z1 = valid ? zq[q].y : 0.f;
-                    const float sz0 = sigmoid_fast(z0), sz1 = sigmoid_fast(z1);
-                    dy0 = do0 * (z0 * sz0);
-                    dy1 = do1 * (z1 * sz1);
-                    if (valid) {   // dz = dout * d silu(z)/dz * y needs nothing from the sweeps
-                        const float f0 = do0 * sz0 * fmaf(z0, 1.0f - sz0, 1.0f), f1 = do1 * sz1 * fmaf(z1, 1.0f - sz1, 1.0f);
-                        stg_pair<T>(dzb + (int64_t)(tb + t) * p.dz_rs, f0 * yq[q].x, f1 * yq[q].y, vec);
+                    float2 z2 = zq[q];
+                    if (!FULL && !valid) z2 = make_float2(0.f, 0.f);
+                    const float2 ez = ex2_2(fmul2(z2, splat2(-kLog2e)));
+                    const float2 den = fadd2(ez, splat2(1.0f));
+                    const float2 sz2 = make_float2(rcp_approx(den.x), rcp_approx(den.y));   // sigmoid(z)
+                    const float2 zs = fmul2(z2, sz2);                                        // silu(z)
+                    dy2 = fmul2(do2, zs);
+                    if (valid) {   // dz = dout * d silu(z)/dz * y needs nothing from the sweeps: d silu = sz (1 + z - z sz)
+                        const float2 w = fadd2(fadd2(z2, splat2(1.0f)), make_float2(-zs.x, -zs.y));
+                        const float2 f = fmul2(fmul2(do2, sz2), fmul2(w, yq[q]));
+                        stg_pair<T>(dzp, f.x, f.y, vec);
                     }
+                    dzp += 4 * p.dz_rs;
                 }
-                sDD[t * NP + ip] = make_float4(dl0, dl0 * u0, dl1, dl1 * u1);
-                sDY[t * NP + ip] = make_float2(dy0, dy1);
-                sEpi[t * NP + ip] = make_float4(u0, sg[q].x, u1, sg[q].y);
+                const float2 dlu = fmul2(dl2, u2);
+                sDD[t * NP + ip] = make_float4(dl2.x, dl2.y, dlu.x, dlu.y);
+                sDY[t * NP + ip] = dy2;
+                sEpi[t * NP + ip] = make_float4(u2.x, u2.y, sg[q].x, sg[q].y);
             }
             // B|C rows as fp32 quads, natural and pair-swapped order: [sw][t][B quads 0..3 | C quads 0..3]
 #pragma unroll
@@ -323,11 +337,15 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
                 sBC[kCBCPlane + tid + q * NT] = make_float4(bcv[q].y, bcv[q].x, bcv[q].w, bcv[q].z);
             }
         };
+        auto phase_a_any = [&](int i, int stage) {
+            if ((klast - i) * kChunk + kChunk <= t1) phase_a(i, stage, std::true_type{});
+            else phase_a(i, stage, std::false_type{});
+        };
 
         GFE_CLK(0);   // unit set-up (incl. waiting for the successor segment's carry)
         cp_async_wait<NST - 1>();
         __syncthreads();
-        phase_a(0, 0);
+        phase_a_any(0, 0);
         GFE_CLK(5);
 
         int stage = 0;   // i % NST
@@ -364,7 +382,7 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
                     const float2 B01 = make_float2(B4.x, B4.y), B23 = make_float2(B4.z, B4.w);
 #pragma unroll
                     for (int ch = 0; ch < 2; ++ch) {
-                        const float2 dl2 = splat2(ch ? dd.z : dd.x), du2 = splat2(ch ? dd.w : dd.y);   // scalar-broadcast operands
+                        const float2 dl2 = splat2(ch ? dd.y : dd.x), du2 = splat2(ch ? dd.w : dd.z);   // scalar-broadcast operands
                         const float2 e0 = ex2_2(fmul2(dl2, A2[ch][0])), e1 = ex2_2(fmul2(dl2, A2[ch][1]));
 #if GFE_CBWD_KEEP_A
                         e0h[ch][j] = e0; e1h[ch][j] = e1;
@@ -395,7 +413,7 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
                         float4 part;
 #pragma unroll
                         for (int ch = 0; ch < 2; ++ch) {
-                            const float2 dl2 = splat2(ch ? dd.z : dd.x), du2 = splat2(ch ? dd.w : dd.y), dy2 = splat2(ch ? dyv.y : dyv.x);
+                            const float2 dl2 = splat2(ch ? dd.y : dd.x), du2 = splat2(ch ? dd.w : dd.z), dy2 = splat2(ch ? dyv.y : dyv.x);
                             const float2 gg0 = ffma2(C01, dy2, G[ch][0]);   // g[t] = C dy + a[t+1] g[t+1]
                             const float2 gg1 = ffma2(C23, dy2, G[ch][1]);
                             if (ch == 0) {
@@ -417,8 +435,8 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
                             const float2 sa = ffma2(w1, A2[ch][1], fmul2(w0, A2[ch][0]));            // sum_n (da a) A log2e
                             dA[ch][0] = ffma2(w0, dl2, dA[ch][0]);                                   // dA[c,n] += (da a) delta
                             dA[ch][1] = ffma2(w1, dl2, dA[ch][1]);
-                            if (ch == 0) { part.x = sb.x + sb.y; part.y = sa.x + sa.y; }
-                            else { part.z = sb.x + sb.y; part.w = sa.x + sa.y; }
+                            if (ch == 0) { part.x = sb.x + sb.y; part.z = sa.x + sa.y; }   // {S1_0, S1_1, S2_0, S2_1}
+                            else { part.y = sb.x + sb.y; part.w = sa.x + sa.y; }
                         }
                         s_w[j * (4 * SPL)] = part;
                         v[4 * jj] = db0.x; v[4 * jj + 1] = db0.y; v[4 * jj + 2] = db1.x; v[4 * jj + 3] = db1.y;
@@ -448,24 +466,29 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
                 // ------------------------------------------------------------ phase C (this warp's 8 pairs x 8 steps)
                 GFE_CLK(2);
                 __syncwarp();
+                {
+                    T *dup = dub + ((int64_t)tb + jo + cr) * p.du_rs, *ddp = ddb + ((int64_t)tb + jo + cr) * p.dd_rs;
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int tl = cr + 4 * q, t = jo + tl;
-                    if (tb + t < t1) {
-                        const float4 *sp4 = sS + (tl * 4) * SPL + cp;   // {S1, S2} of both channels, one plane per quad
-                        const float4 p0 = sp4[0], p1 = sp4[SPL], p2 = sp4[2 * SPL], p3 = sp4[3 * SPL];
-                        const float s1a = (p0.x + p1.x) + (p2.x + p3.x), s2a = ((p0.y + p1.y) + (p2.y + p3.y)) * kLn2;
-                        const float s1b = (p0.z + p1.z) + (p2.z + p3.z), s2b = ((p0.w + p1.w) + (p2.w + p3.w)) * kLn2;
-                        const float4 dd = sDD[t * NP + cp];
-                        const float2 dy = sDY[t * NP + cp];
-                        const float4 e4 = sEpi[t * NP + cp];
-                        const float draw0 = fmaf(s1a, e4.x, s2a) * e4.y, draw1 = fmaf(s1b, e4.z, s2b) * e4.w;   // d delta through softplus
-                        stg_pair<T>(dub + (int64_t)(tb + t) * p.du_rs, fmaf(dd.x, s1a, Dc.x * dy.x), fmaf(dd.z, s1b, Dc.y * dy.y), vec);
-                        stg_pair<T>(ddb + (int64_t)(tb + t) * p.dd_rs, draw0, draw1, vec);
-                        dD_acc.x = fmaf(dy.x, e4.x, dD_acc.x);
-                        dD_acc.y = fmaf(dy.y, e4.z, dD_acc.y);
-                        dbias_acc.x += draw0;
-                        dbias_acc.y += draw1;
+                    for (int q = 0; q < 2; ++q) {
+                        const int tl = cr + 4 * q, t = jo + tl;
+                        if (tb + t < t1) {
+                            const float4 *sp4 = sS + (tl * 4) * SPL + cp;   // {S1_0, S1_1, S2_0, S2_1}, one plane per quad
+                            const float4 p0 = sp4[0], p1 = sp4[SPL], p2 = sp4[2 * SPL], p3 = sp4[3 * SPL];
+                            const float4 dd = sDD[t * NP + cp];
+                            const float2 dy = sDY[t * NP + cp];
+                            const float4 e4 = sEpi[t * NP + cp];
+                            const float2 s1 = fadd2(fadd2(make_float2(p0.x, p0.y), make_float2(p1.x, p1.y)), fadd2(make_float2(p2.x, p2.y), make_float2(p3.x, p3.y)));
+                            const float2 s2 = fmul2(fadd2(fadd2(make_float2(p0.z, p0.w), make_float2(p1.z, p1.w)), fadd2(make_float2(p2.z, p2.w), make_float2(p3.z, p3.w))), splat2(kLn2));
+                            const float2 u2 = make_float2(e4.x, e4.y);
+                            const float2 draw = fmul2(ffma2(s1, u2, s2), make_float2(e4.z, e4.w));   // d delta through softplus
+                            const float2 du = ffma2(make_float2(dd.x, dd.y), s1, fmul2(Dc, dy));
+                            stg_pair<T>(dup, du.x, du.y, vec);
+                            stg_pair<T>(ddp, draw.x, draw.y, vec);
+                            dD_acc = ffma2(dy, u2, dD_acc);
+                            dbias_acc = fadd2(dbias_acc, draw);
+                        }
+                        dup += 4 * p.du_rs;
+                        ddp += 4 * p.dd_rs;
                     }
                 }
                 __syncwarp();   // the next half overwrites the partial planes
@@ -495,7 +518,7 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
                 }
             }
             GFE_CLK(4);
-            if (i + 1 < nch) phase_a(i + 1, stage);
+            if (i + 1 < nch) phase_a_any(i + 1, stage);
             GFE_CLK(5);
         }
 
@@ -616,8 +639,7 @@ static int launch_bwd_chain_t(const gfe_selscan_args *a, cudaStream_t st) {
     ChainSched cs{};
     rc = chain_fill_sched(cs, ws, a->batch, a->d_inner, pl, st);
     if (rc != GFE_OK) return rc;
-    const int cpb = chain_cpb(a, true);
-    if (chain_pair_stores(a, true)) p.flags |= kFlagPairStores;
+    const int cpb = (chain_cpb(a, true) == 16 && chain_pair_stores(a, true)) ? 16 : 0;   // 16: cp.async staging AND paired stores
     if (pl.independent && nseg > 1) {
         ScopedKernelTimer tm(K_SELSCAN_BWD_SUMMARY, st);
         rc = seg_launch_carries(p, cs, a->dtype, cpc, true, a->z != nullptr, cpb, st);

@@ -214,8 +214,7 @@ static int launch_fwd_chain_t(const gfe_selscan_args *a, cudaStream_t st) {
     ChainSched cs{};
     rc = chain_fill_sched(cs, reinterpret_cast<char *>(a->ws), a->batch, a->d_inner, pl, st);
     if (rc != GFE_OK) return rc;
-    if (chain_pair_stores(a, false)) p.flags |= kFlagPairStores;
-    const int cpb = chain_cpb(a, false);
+    const int cpb = (chain_cpb(a, false) == 16 && chain_pair_stores(a, false)) ? 16 : 0;   // 16: cp.async staging AND paired stores
     if (pl.independent && pl.nseg > 1) {
         ScopedKernelTimer tm(K_SELSCAN_FWD_SUMMARY, st);
         rc = seg_launch_carries(p, cs, a->dtype, pl.cpc, false, false, cpb, st);

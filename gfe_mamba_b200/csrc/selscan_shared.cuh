@@ -36,7 +36,6 @@ struct ScanParams {
     int bc_interleaved;   // part_bc rows are {dB[n], dC[n]} pairs (v2 backward) instead of dB[16] | dC[16]
 };
 
-constexpr uint32_t kFlagPairStores = 1u << 16;   // internal: every output base / stride allows paired (2-channel) stores
 constexpr int kPairs = kNState / 2;
 constexpr int kRedStride = 34;  // padded row of the reduced dB|dC tile (bank-conflict free float2 writes)
 
@@ -240,6 +239,14 @@ template <> __device__ __forceinline__ __half2 pair_from_f<__half>(float a, floa
 template <typename T> __device__ __forceinline__ float2 lds_pair(const T *row, int i) {
     return pair_to_f(reinterpret_cast<const typename Pair<T>::type *>(row)[i]);
 }
+// four consecutive elements of a shared tile (8- / 16-byte aligned) as fp32: one load
+__device__ __forceinline__ float4 lds_quad(const float *src) { return *reinterpret_cast<const float4 *>(src); }
+__device__ __forceinline__ float4 lds_quad(const __nv_bfloat16 *src) { return ckpt_load_smem(src); }
+__device__ __forceinline__ float4 lds_quad(const __half *src) {
+    const uint2 r = *reinterpret_cast<const uint2 *>(src);
+    const float2 lo = __half22float2(*reinterpret_cast<const __half2 *>(&r.x)), hi = __half22float2(*reinterpret_cast<const __half2 *>(&r.y));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
 // streaming store of two adjacent channels; `vec` says whether the destination allows one paired store
 template <typename T> __device__ __forceinline__ void stg_pair(T *dst, float a, float b, bool vec) {
     if (vec) {
@@ -327,7 +334,7 @@ static int persistent_grid(int nt, size_t smem, int total) {
 #define GFE_CBWD_MINB 2        // backward: CTAs of 128 threads per SM the register budget is set for (2: 255 registers, 3: 168)
 #endif
 #ifndef GFE_SEG_UNITS_PER_CTA
-#define GFE_SEG_UNITS_PER_CTA 3   // independent segments: units per resident CTA the plan aims for
+#define GFE_SEG_UNITS_PER_CTA 2   // independent segments: units per resident CTA the plan aims for
 #endif
 struct ChainPlan {
     int cpc, nblk;          // channel-block width and count

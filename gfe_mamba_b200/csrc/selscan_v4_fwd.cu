@@ -13,6 +13,8 @@
 //     state-steps (v2: 3 LDS.128 + 8 + 4 + 1 for 4).
 // Segment chaining (ChainSched); checkpoints [b][t/8][c][16] (fp32, bf16 for bf16 activations) and the saved y are what
 // selscan_chain_bwd.cu consumes.
+#include <type_traits>
+
 #include "common.cuh"
 #include "selscan_shared.cuh"
 
@@ -79,7 +81,7 @@ __device__ __forceinline__ void v4_recur_chunk(const float4 *__restrict__ dd_r, 
         float yv[2];
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
-            const float dl = ch ? dd.z : dd.x, du = ch ? dd.w : dd.y;
+            const float dl = ch ? dd.y : dd.x, du = ch ? dd.w : dd.z;
             const float2 x0 = fmul2(splat2(dl), A2[ch][0]), x1 = fmul2(splat2(dl), A2[ch][1]);
             // GFE_V4_POLY of every 8 exps of a step run as a polynomial on the FMA pipe instead of MUFU.EX2
             const float2 a0 = (GFE_V4_POLY >= 1 && ch == 0 && (j & 1)) ? ex2_poly2(x0) : ex2_2(x0);
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(2 * CPC, GFE_V4_MINB * (64 / CPC)) selscan_fwd
     float4 *sBC = reinterpret_cast<float4 *>(smem + SM::kOffBC);
     float2 *sY = reinterpret_cast<float2 *>(smem + SM::kOffY);
     const bool sp = p.flags & GFE_FLAG_DELTA_SOFTPLUS;
-    const bool vec = p.flags & kFlagPairStores;
+    constexpr bool vec = CPB == 16;   // the cp.async instantiation also requires pair-aligned outputs (chain_launch_fwd)
     const int per_seg = p.B * cs.nblk;
 
     const float4 *dd_r = sDD + rp;
@@ -157,19 +159,13 @@ __global__ void __launch_bounds__(2 * CPC, GFE_V4_MINB * (64 / CPC)) selscan_fwd
         CK *ckq = p.ckpt ? reinterpret_cast<CK *>(p.ckpt) + ((size_t)b * p.nchunks * p.ED + c0 + 2 * rp) * kNState + 4 * rq : nullptr;
         const size_t ck_step = (size_t)p.ED * kNState;   // elements between consecutive checkpoints
 
-        // per-thread source pointers of the staged pieces at row t0 (advanced by 16 rows per chunk)
-        const char *su, *sd, *sz = nullptr, *sbc[BCI];
-        int64_t adv_u, adv_d, adv_z = 0, adv_bc[BCI];
+        // per-thread source pointers of the staged pieces of the NEXT chunk to issue (chunks are issued strictly in order)
+        const char *su = nullptr, *sd = nullptr, *sz = nullptr, *sbc[BCI];
         int bcrow[BCI];
         if constexpr (CPB == 16) {
             su = reinterpret_cast<const char *>(ub + (int64_t)(t0 + srow) * p.u_rs) + spiece * 16;
             sd = reinterpret_cast<const char *>(db + (int64_t)(t0 + srow) * p.d_rs) + spiece * 16;
-            adv_u = (int64_t)kChunk * p.u_rs * (int64_t)sizeof(T);
-            adv_d = (int64_t)kChunk * p.d_rs * (int64_t)sizeof(T);
-            if (HAS_Z) {
-                sz = reinterpret_cast<const char *>(zb + (int64_t)(t0 + srow) * p.z_rs) + spiece * 16;
-                adv_z = (int64_t)kChunk * p.z_rs * (int64_t)sizeof(T);
-            }
+            if (HAS_Z) sz = reinterpret_cast<const char *>(zb + (int64_t)(t0 + srow) * p.z_rs) + spiece * 16;
 #pragma unroll
             for (int i = 0; i < BCI; ++i) {
                 const int pc = tid + i * NT;                    // < 2 * BCP checked at issue time
@@ -177,7 +173,6 @@ __global__ void __launch_bounds__(2 * CPC, GFE_V4_MINB * (64 / CPC)) selscan_fwd
                 bcrow[i] = within / (BCP / kChunk);
                 const int64_t rs = sel ? p.C_rs : p.B_rs;
                 sbc[i] = reinterpret_cast<const char *>((sel ? Cb : Bb) + (int64_t)(t0 + bcrow[i]) * rs) + (within % (BCP / kChunk)) * 16;
-                adv_bc[i] = (int64_t)kChunk * rs * (int64_t)sizeof(T);
             }
         }
         const uint32_t dst_act = smem_u32(smem) + srow * RB + spiece * 16;
@@ -192,14 +187,19 @@ __global__ void __launch_bounds__(2 * CPC, GFE_V4_MINB * (64 / CPC)) selscan_fwd
                     if (srow < nrows) {
 #pragma unroll
                         for (int i = 0; i < PPT; ++i) {
-                            cp_async<16>(dst_act + so + i * 16, su + (int64_t)k * adv_u + i * 16);
-                            cp_async<16>(dst_act + so + SM::kTile + i * 16, sd + (int64_t)k * adv_d + i * 16);
-                            if (HAS_Z) cp_async<16>(dst_act + so + 2 * SM::kTile + i * 16, sz + (int64_t)k * adv_z + i * 16);
+                            cp_async<16>(dst_act + so + i * 16, su + i * 16);
+                            cp_async<16>(dst_act + so + SM::kTile + i * 16, sd + i * 16);
+                            if (HAS_Z) cp_async<16>(dst_act + so + 2 * SM::kTile + i * 16, sz + i * 16);
                         }
                     }
 #pragma unroll
                     for (int i = 0; i < BCI; ++i)
-                        if (tid + i * NT < 2 * BCP && bcrow[i] < nrows) cp_async<16>(dst_bc + so + i * NT * 16, sbc[i] + (int64_t)k * adv_bc[i]);
+                        if (tid + i * NT < 2 * BCP && bcrow[i] < nrows) cp_async<16>(dst_bc + so + i * NT * 16, sbc[i]);
+                    constexpr int64_t sz_t = (int64_t)sizeof(T) * kChunk;
+                    su += p.u_rs * sz_t; sd += p.d_rs * sz_t;
+                    if (HAS_Z) sz += p.z_rs * sz_t;
+#pragma unroll
+                    for (int i = 0; i < BCI; ++i) sbc[i] += ((tid + i * NT) / BCP ? p.C_rs : p.B_rs) * sz_t;
                 } else {
                     unsigned char *s = smem + so;
                     stage_tile<T, 0, CPC, NT>(s, ub + (int64_t)tb * p.u_rs, p.u_rs, nrows, tid);
@@ -248,7 +248,9 @@ __global__ void __launch_bounds__(2 * CPC, GFE_V4_MINB * (64 / CPC)) selscan_fwd
         }
 
         float2 Du[4], gate[4];
-        auto phase_a = [&](int k, int stage) {   // per-(t, channel pair) scalars of chunk k -> shared slots; B|C rows -> fp32 quads
+        // FULL: all 16 rows of the chunk lie inside the sequence (every chunk but a ragged last one): no row masking.
+        auto phase_a = [&](int k, int stage, auto full_c) {   // per-(t, channel pair) scalars of chunk k -> shared slots; B|C rows -> fp32 quads
+            constexpr bool FULL = decltype(full_c)::value;
             const int tb = t0 + k * kChunk;
             const unsigned char *s = smem + stage * SM::kStage;
             const T *sU = reinterpret_cast<const T *>(s);
@@ -257,12 +259,13 @@ __global__ void __launch_bounds__(2 * CPC, GFE_V4_MINB * (64 / CPC)) selscan_fwd
             const T *sBr = reinterpret_cast<const T *>(s + NTILE * SM::kTile);   // B rows then C rows
             float2 dl[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {   // branch-free packed softplus (selscan_shared.cuh)
-                const float2 d2 = lds_pair(sD + (ir + 4 * i) * CPC, ip);
-                const float2 x = fadd2(d2, bias);
-                float2 sg2;
-                const float2 v = softplus_pair<false>(x, sg2);
-                dl[i] = sp ? v : x;
+            for (int i = 0; i < 4; ++i) dl[i] = fadd2(lds_pair(sD + (ir + 4 * i) * CPC, ip), bias);
+            if (sp) {   // branch-free packed softplus (selscan_shared.cuh)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float2 sg2;
+                    dl[i] = softplus_pair<false>(dl[i], sg2);
+                }
             }
             float2 uq[4], zq[4];   // every load of the phase before its first store (an LDS is never moved above an STS)
 #pragma unroll
@@ -276,34 +279,34 @@ __global__ void __launch_bounds__(2 * CPC, GFE_V4_MINB * (64 / CPC)) selscan_fwd
             for (int i = 0; i < BCC; ++i) {   // B|C rows -> fp32 quads: [t][B quads 0..3 | C quads 0..3]
                 const int e = tid + i * NT, t = e >> 3, q8 = e & 7;
                 bcv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (tb + t < t1) {
-                    const T *src = sBr + (q8 < 4 ? 0 : kChunk * 16) + t * 16 + 4 * (q8 & 3);
-                    const float2 lo = lds_pair(src, 0), hi = lds_pair(src, 1);
-                    bcv[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
-                }
+                if (FULL || tb + t < t1) bcv[i] = lds_quad(sBr + (q8 < 4 ? 0 : kChunk * 16) + t * 16 + 4 * (q8 & 3));
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int t = ir + 4 * i;
-                const bool valid = tb + t < t1;
-                const float2 u2 = uq[i];
-                const float u0 = valid ? u2.x : 0.f, u1 = valid ? u2.y : 0.f;
-                const float dl0 = valid ? dl[i].x : 0.f, dl1 = valid ? dl[i].y : 0.f;   // padded step: a = 1, bx = 0
-                sDD[t * NP + ip] = make_float4(dl0, dl0 * u0, dl1, dl1 * u1);
-                Du[i] = make_float2(Dc.x * u0, Dc.y * u1);
+                float2 u2 = uq[i], dl2 = dl[i];
+                if (!FULL && tb + t >= t1) u2 = dl2 = make_float2(0.f, 0.f);   // padded step: a = 1, bx = 0
+                const float2 dlu = fmul2(dl2, u2);
+                sDD[t * NP + ip] = make_float4(dl2.x, dl2.y, dlu.x, dlu.y);
+                Du[i] = fmul2(Dc, u2);
                 if (HAS_Z) {
                     const float2 z2 = zq[i];
-                    gate[i] = make_float2(z2.x * sigmoid_fast(z2.x), z2.y * sigmoid_fast(z2.y));
+                    const float2 den = fadd2(ex2_2(fmul2(z2, splat2(-kLog2e))), splat2(1.0f));
+                    gate[i] = fmul2(z2, make_float2(rcp_approx(den.x), rcp_approx(den.y)));
                 }
             }
 #pragma unroll
             for (int i = 0; i < BCC; ++i) sBC[tid + i * NT] = bcv[i];
         };
+        auto phase_a_any = [&](int k, int stage) {
+            if (t0 + (k + 1) * kChunk <= t1) phase_a(k, stage, std::true_type{});
+            else phase_a(k, stage, std::false_type{});
+        };
 
         GFE_CLK(0);   // unit set-up (incl. waiting for the predecessor segment)
         cp_async_wait<NST - 1>();
         __syncthreads();
-        phase_a(0, 0);
+        phase_a_any(0, 0);
         GFE_CLK(5);
         // running output pointers of this thread's item rows (row ir of the current chunk)
         T *op = ob + (int64_t)(t0 + ir) * p.o_rs;
@@ -340,7 +343,7 @@ __global__ void __launch_bounds__(2 * CPC, GFE_V4_MINB * (64 / CPC)) selscan_fwd
                 if (yp_g != nullptr) yp_g += y_step;
             }
             GFE_CLK(4);
-            if (k + 1 < nch) phase_a(k + 1, stage);
+            if (k + 1 < nch) phase_a_any(k + 1, stage);
             GFE_CLK(5);
         }
 
