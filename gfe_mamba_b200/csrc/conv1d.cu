@@ -12,7 +12,13 @@
 
 namespace gfe {
 
-constexpr int kConvTile = 128;  // time steps per thread (one partial dw|dbias row per tile)
+#ifndef GFE_CONV_TILE
+#define GFE_CONV_TILE 128
+#endif
+#ifndef GFE_CONV_PREFETCH
+#define GFE_CONV_PREFETCH 1   // the next group's rows are requested before the current group is computed
+#endif
+constexpr int kConvTile = GFE_CONV_TILE;  // time steps per thread (one partial dw|dbias row per tile)
 
 struct ConvParams {
     const void *xin, *du;
@@ -63,12 +69,20 @@ __global__ void __launch_bounds__(128) conv1d_silu_fwd_kernel(ConvParams p) {
         for (int i = 0; i < V; ++i) win[i][k + 1] = t >= 0 ? xv.get(i) : 0.f;
     }
     constexpr int U = 8;
+    ChanVec<T, V> xn[U];   // rows of the next group, in flight while the current group is computed
+#pragma unroll
+    for (int j = 0; j < U; ++j) xn[j] = ChanVec<T, V>::load(x + (int64_t)min(t0 + j, t1 - 1) * p.x_rs);
     for (int tb = t0; tb < t1; tb += U) {
         ChanVec<T, V> xr[U];
 #pragma unroll
-        for (int j = 0; j < U; ++j) xr[j] = ChanVec<T, V>::load(x + (int64_t)min(tb + j, t1 - 1) * p.x_rs);
+        for (int j = 0; j < U; ++j) xr[j] = xn[j];
+        if (GFE_CONV_PREFETCH && tb + U < t1) {
+#pragma unroll
+            for (int j = 0; j < U; ++j) xn[j] = ChanVec<T, V>::load(x + (int64_t)min(tb + U + j, t1 - 1) * p.x_rs);
+        }
 #pragma unroll
         for (int j = 0; j < U; ++j) {
+            if (!GFE_CONV_PREFETCH && tb > t0) xr[j] = ChanVec<T, V>::load(x + (int64_t)min(tb + j, t1 - 1) * p.x_rs);
             if (tb + j < t1) {
                 ChanVec<T, V> o;
 #pragma unroll
@@ -121,17 +135,32 @@ __global__ void __launch_bounds__(128) conv1d_silu_bwd_kernel(ConvParams p) {
     // dv is needed K-1 steps past the tile to finish dxin of the tile's last steps
     const int tend = t1 + (K - 1);
     constexpr int U = 8;
+    ChanVec<T, V> xn[U], gn[U];   // rows of the next group, in flight while the current group is computed
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+        const int t = min(t0 + j, p.L - 1);
+        xn[j] = ChanVec<T, V>::load(x + (int64_t)t * p.x_rs);
+        gn[j] = ChanVec<T, V>::load(du + (int64_t)t * p.du_rs);
+    }
     for (int tb = t0; tb < tend; tb += U) {
         ChanVec<T, V> xr[U], gr[U];
 #pragma unroll
-        for (int j = 0; j < U; ++j) {
-            const int t = min(tb + j, p.L - 1);
-            xr[j] = ChanVec<T, V>::load(x + (int64_t)t * p.x_rs);
-            gr[j] = ChanVec<T, V>::load(du + (int64_t)t * p.du_rs);
+        for (int j = 0; j < U; ++j) { xr[j] = xn[j]; gr[j] = gn[j]; }
+        if (GFE_CONV_PREFETCH && tb + U < tend) {
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                const int t = min(tb + U + j, p.L - 1);
+                xn[j] = ChanVec<T, V>::load(x + (int64_t)t * p.x_rs);
+                gn[j] = ChanVec<T, V>::load(du + (int64_t)t * p.du_rs);
+            }
         }
 #pragma unroll
         for (int j = 0; j < U; ++j) {
             const int t = tb + j;
+            if (!GFE_CONV_PREFETCH && tb > t0) {
+                xr[j] = ChanVec<T, V>::load(x + (int64_t)min(t, p.L - 1) * p.x_rs);
+                gr[j] = ChanVec<T, V>::load(du + (int64_t)min(t, p.L - 1) * p.du_rs);
+            }
             if (t < tend) {
                 const int s_out = t - (K - 1);   // dxin[s] = sum_k w[k] dv[s + K-1 - k]
                 ChanVec<T, V> o;

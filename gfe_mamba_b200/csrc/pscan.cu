@@ -198,6 +198,173 @@ __global__ void __launch_bounds__(128) pscan_bwd_kernel(PscanParams p) {
     }
 }
 
+// shared-memory accesses the compiler may neither cache in registers nor reorder across the ready flags
+__device__ __forceinline__ float4 ps_ld_shared(const float4 *p) {
+    float4 v;
+    asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ float2 ps_ld_shared(const float2 *p) {
+    float2 v;
+    asm volatile("ld.volatile.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ps_ld_shared(const float *p) {
+    float v;
+    asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void ps_st_shared(float4 *p, float4 v) {
+    asm volatile("st.volatile.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void ps_st_shared(float2 *p, float2 v) {
+    asm volatile("st.volatile.shared.v2.f32 [%0], {%1, %2};" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void ps_st_shared(float *p, float v) {
+    asm volatile("st.volatile.shared.f32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "f"(v) : "memory");
+}
+
+// ---- warp-chained single pass --------------------------------------------------------------------------------------
+// The sequential kernels above keep one batch of U steps in flight per thread and wait out a full memory round trip per batch:
+// with few columns (B * D * N / 4 threads) that is latency-, not bandwidth-bound (forward 47-65 % of the HBM peak, round 2).
+// Here the W warps of a CTA share the same 32 * V columns and take the batches of U steps in turn (warp w: batches w, w + W,
+// ...).  A warp loads its batch, scans it locally from a zero carry while keeping the running products (both in place of the
+// loaded values), and only then needs the carry of the previous batch: it picks it up from shared memory, publishes its own end
+// state -- one FMA later, so the serial chain per batch is a shared-memory hop instead of a memory round trip plus U dependent
+// FMAs -- and fixes its U outputs up with one FMA each.  W batches per column are in flight, every element is still read and
+// written exactly once, and nothing is recomputed.  (A shared-memory ring filled by cp.async.bulk -- one warp per 32 float4
+// columns, 512-byte row pieces, up to 24 stages of 8 steps -- was measured as well: 71 % / 35 % of the HBM peak at B = 8 / 2
+// against 77 % / 53 % for this kernel; many small bulk copies do not reach the memory-level parallelism of plain loads.)
+template <int V, int U, int W>
+__global__ void __launch_bounds__(32 * W) pscan_fwd_chain_kernel(PscanParams p) {
+    using VT = typename Vec<V>::type;
+    __shared__ VT s_carry[W][32];
+    __shared__ int s_ready[W];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t nvec = p.DN / V;
+    const int64_t i = (int64_t)blockIdx.x * 32 + lane;
+    const bool act = i < nvec;
+    const int64_t ic = act ? i : nvec - 1;
+    const int b = blockIdx.z;
+    const VT *A = reinterpret_cast<const VT *>(p.A + (size_t)b * p.L * p.DN) + ic;
+    const VT *X = reinterpret_cast<const VT *>(p.X + (size_t)b * p.L * p.DN) + ic;
+    VT *H = reinterpret_cast<VT *>(p.Hout + (size_t)b * p.L * p.DN) + ic;
+    if (lane == 0) s_ready[w] = -1;
+    __syncthreads();
+    const int nb = (p.L + U - 1) / U;
+    const int wp = (w + W - 1) % W;
+    volatile int *ready = s_ready;
+    for (int k = w; k < nb; k += W) {
+        const int tb = k * U;
+        VT a[U], x[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int t = min(tb + j, p.L - 1);
+            a[j] = __ldcs(A + (size_t)t * nvec);
+            x[j] = __ldcs(X + (size_t)t * nvec);
+        }
+#pragma unroll
+        for (int j = 1; j < U; ++j) {   // x[j] <- state after step j from a zero carry, a[j] <- a[0] ... a[j]
+            x[j] = Vec<V>::fma(a[j], x[j - 1], x[j]);
+            a[j] = Vec<V>::mul(a[j], a[j - 1]);
+        }
+        VT hin = Vec<V>::zero();
+        if (k > 0) {
+            while (ready[wp] != k - 1) { }
+            __syncwarp();
+            hin = ps_ld_shared(&s_carry[wp][lane]);
+        }
+        if (k + 1 < nb) {   // the end state of this batch, as early as possible
+            ps_st_shared(&s_carry[w][lane], Vec<V>::fma(a[U - 1], hin, x[U - 1]));
+            __syncwarp();
+            if (lane == 0) { __threadfence_block(); ready[w] = k; }
+        }
+        if (act) {
+#pragma unroll
+            for (int j = 0; j < U; ++j)
+                if (tb + j < p.L) __stcs(H + (size_t)(tb + j) * nvec, Vec<V>::fma(a[j], hin, x[j]));
+        }
+    }
+}
+
+// Reverse direction: gt[t] = dH[t] + A[t+1] gt[t+1], dX[t] = gt[t], dA[t] = H[t-1] gt[t]; the carry handed to the earlier batch
+// is G = A[tb] gt[tb].  Within a batch gt[j] = gl[j] + Q[j] G_in with gl the local scan and Q[j] = A[j+1] ... A[U-1].
+template <int V, int U, int W>
+__global__ void __launch_bounds__(32 * W) pscan_bwd_chain_kernel(PscanParams p) {
+    using VT = typename Vec<V>::type;
+    __shared__ VT s_carry[W][32];
+    __shared__ int s_ready[W];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t nvec = p.DN / V;
+    const int64_t i = (int64_t)blockIdx.x * 32 + lane;
+    const bool act = i < nvec;
+    const int64_t ic = act ? i : nvec - 1;
+    const int b = blockIdx.z;
+    const VT *A = reinterpret_cast<const VT *>(p.A + (size_t)b * p.L * p.DN) + ic;
+    const VT *dH = reinterpret_cast<const VT *>(p.dH + (size_t)b * p.L * p.DN) + ic;
+    const VT *H = reinterpret_cast<const VT *>(p.H + (size_t)b * p.L * p.DN) + ic;
+    VT *dA = reinterpret_cast<VT *>(p.dA + (size_t)b * p.L * p.DN) + ic;
+    VT *dX = reinterpret_cast<VT *>(p.dX + (size_t)b * p.L * p.DN) + ic;
+    if (lane == 0) s_ready[w] = -1;
+    __syncthreads();
+    const int nb = (p.L + U - 1) / U;
+    const int wp = (w + W - 1) % W;
+    volatile int *ready = s_ready;
+    for (int k = w; k < nb; k += W) {   // k-th batch in processing order = batch nb - 1 - k of the sequence
+        const int tb = (nb - 1 - k) * U;
+        VT a[U], g[U], hp[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int t = min(tb + j, p.L - 1);
+            a[j] = __ldcs(A + (size_t)t * nvec);
+            g[j] = tb + j < p.L ? __ldcs(dH + (size_t)t * nvec) : Vec<V>::zero();   // steps past the end contribute nothing
+            hp[j] = t > 0 ? __ldcs(H + (size_t)(t - 1) * nvec) : Vec<V>::zero();
+        }
+        // g[j] <- local gt[j]; a[j + 1] <- Q[j] = a[j + 1] ... a[U - 1] (Q[U - 1] = 1 stays implicit); a[0] is kept for the carry
+        VT q = Vec<V>::one();
+#pragma unroll
+        for (int j = U - 2; j >= 0; --j) {
+            g[j] = Vec<V>::fma(a[j + 1], g[j + 1], g[j]);
+            q = Vec<V>::mul(q, a[j + 1]);
+            a[j + 1] = q;
+        }
+        VT gin = Vec<V>::zero();
+        if (k > 0) {
+            while (ready[wp] != k - 1) { }
+            __syncwarp();
+            gin = ps_ld_shared(&s_carry[wp][lane]);
+        }
+        if (k + 1 < nb) {   // G handed to the earlier batch: a[0] (gl[0] + Q[0] G_in)
+            const VT q0 = U > 1 ? a[1] : Vec<V>::one();
+            ps_st_shared(&s_carry[w][lane], Vec<V>::mul(a[0], Vec<V>::fma(q0, gin, g[0])));
+            __syncwarp();
+            if (lane == 0) { __threadfence_block(); ready[w] = k; }
+        }
+        if (act) {
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                if (tb + j < p.L) {
+                    const VT gt = j + 1 < U ? Vec<V>::fma(a[j + 1], gin, g[j]) : Vec<V>::add(g[j], gin);
+                    __stcs(dX + (size_t)(tb + j) * nvec, gt);
+                    __stcs(dA + (size_t)(tb + j) * nvec, Vec<V>::mul(hp[j], gt));
+                }
+            }
+        }
+    }
+}
+
+#ifndef GFE_PSCAN_CHAIN
+#define GFE_PSCAN_CHAIN 1
+#endif
+#ifndef GFE_PSCAN_FW
+#define GFE_PSCAN_FW 8   // warps per CTA (batches in flight per column), forward
+#endif
+#ifndef GFE_PSCAN_BW
+#define GFE_PSCAN_BW 4   // backward
+#endif
+constexpr int kPsChainU = 8;
+static bool pscan_use_chain(int L, int nseg) { return GFE_PSCAN_CHAIN && nseg == 1 && L >= 4 * kPsChainU; }
+
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 static int pscan_check(const void *a, const void *b, const void *c, int B, int L, int D, int N) {
@@ -247,6 +414,14 @@ GFE_API int gfe_pscan_fwd(const float *A, const float *X, float *H, int B, int L
         rc = check_launch("pscan_fwd_summary");
         if (rc != GFE_OK) return rc;
     }
+    if (pscan_use_chain(L, pl.nseg)) {
+        const int Vc = (al && DN % 4 == 0) ? 4 : 1;
+        const dim3 gridc((unsigned)ceil_div64(DN / Vc, 32), 1, B);
+        ScopedKernelTimer tm(K_PSCAN_FWD, st);
+        if (Vc == 4) pscan_fwd_chain_kernel<4, kPsChainU, GFE_PSCAN_FW><<<gridc, 32 * GFE_PSCAN_FW, 0, st>>>(p);
+        else pscan_fwd_chain_kernel<1, kPsChainU, GFE_PSCAN_FW><<<gridc, 32 * GFE_PSCAN_FW, 0, st>>>(p);
+        return check_launch("pscan_fwd (chained)");
+    }
     { ScopedKernelTimer tm(K_PSCAN_FWD, st);
       if (V == 4 && deep) pscan_fwd_kernel<4, 16, false><<<grid, block, 0, st>>>(p);
       else if (V == 4) pscan_fwd_kernel<4, 8, false><<<grid, block, 0, st>>>(p);
@@ -282,6 +457,14 @@ GFE_API int gfe_pscan_bwd(const float *A, const float *H, const float *dH, float
           else pscan_bwd_kernel<1, 32, true><<<grid, block, 0, st>>>(p); }
         rc = check_launch("pscan_bwd_summary");
         if (rc != GFE_OK) return rc;
+    }
+    if (pscan_use_chain(L, pl.nseg)) {
+        const int Vc = (al && DN % 4 == 0) ? 4 : 1;
+        const dim3 gridc((unsigned)ceil_div64(DN / Vc, 32), 1, B);
+        ScopedKernelTimer tm(K_PSCAN_BWD, st);
+        if (Vc == 4) pscan_bwd_chain_kernel<4, kPsChainU, GFE_PSCAN_BW><<<gridc, 32 * GFE_PSCAN_BW, 0, st>>>(p);
+        else pscan_bwd_chain_kernel<1, kPsChainU, GFE_PSCAN_BW><<<gridc, 32 * GFE_PSCAN_BW, 0, st>>>(p);
+        return check_launch("pscan_bwd (chained)");
     }
     const dim3 grid((unsigned)ceil_div64(nvec, 128), pl.nseg, B);
     { ScopedKernelTimer tm(K_PSCAN_BWD, st);
