@@ -180,6 +180,10 @@ class MambaBlock(nn.Module):
     def forward(self, x):
         # x : (B, L, D) -> (B, L, D)          mamba.py:197-225
         xz = self.in_proj(x)                                  # (B, L, 2*ED)   GEMM
+        if self._inner_fusable(xz):                           # conv -> x_proj -> dt_proj -> scan -> gate as one autograd node
+            y = ops.mamba_inner_fn(xz, self.conv1d.weight, self.conv1d.bias, self.x_proj.weight, self.dt_proj.weight,
+                                   self.dt_proj.bias, self.A_log, self.D)
+            return self.out_proj(y)                           # GEMM
         xin, z = xz.chunk(2, dim=-1)                          # strided halves, consumed in place by the kernels
         if 2 <= self.config.d_conv <= 4:
             u = ops.causal_conv1d_silu(xin, self.conv1d.weight, self.conv1d.bias)   # conv + bias + SiLU fused (:208-212)
@@ -187,6 +191,13 @@ class MambaBlock(nn.Module):
             u = F.silu(self.conv1d(xin.transpose(1, 2))[:, :, :x.shape[1]].transpose(1, 2))
         y = self._ssm_fused(u, z)                             # scan + D skip + SiLU(z) gate fused (:213-222)
         return self.out_proj(y)                               # GEMM
+
+    def _inner_fusable(self, xz):
+        """The one-node inner path serves the shapes the fused kernels are compiled for and the plain configuration (no
+        inner layernorms); everything else takes the op-by-op composition below."""
+        cfg = self.config
+        return (xz.is_cuda and xz.dim() == 3 and cfg.d_state == 16 and 2 <= cfg.d_conv <= 4 and not cfg.inner_layernorms
+                and xz.dtype in (torch.float32, torch.bfloat16, torch.float16) and self.x_proj.bias is None)
 
     def _project(self, x):
         """x_proj / split / optional layernorms / dt_proj without bias (mamba.py:235-238).  delta comes out

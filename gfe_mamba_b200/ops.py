@@ -295,6 +295,129 @@ def causal_conv1d_silu(xin: torch.Tensor, weight: torch.Tensor, bias: Optional[t
     return _CausalConv1dSiluFn.apply(xin, weight, bias)
 
 
+# ------------------------------------------------ conv -> x_proj -> dt_proj -> scan as ONE autograd node
+class _MambaInnerFn(torch.autograd.Function):
+    """MambaBlock.forward between in_proj and out_proj (cross_atten/mamba.py:204-223: split, conv1d + SiLU, x_proj, split,
+    dt_proj, selective scan, gate) as one autograd node.  The kernels are the ones behind causal_conv1d_silu and
+    selective_scan_fn; what the node removes is torch glue between them:
+      * the u|z halves of in_proj's output and the delta|B|C slices of x_proj's output are consumed in place (as before), and in
+        backward their gradients are WRITTEN in place -- dz and d(conv input) into the two halves of one (B, L, 2 ED) tensor,
+        dB / dC into the slices of one (B L, R + 2 N) tensor -- instead of being concatenated by autograd's split backward
+        (a zero-fill plus two copies of 2 ED columns per token);
+      * the two gradients that flow into the conv output (from the scan and from x_proj) meet in the GEMM epilogue
+        (addmm_ with beta = 1) instead of a separate elementwise add over (B, L, ED).
+    """
+
+    @staticmethod
+    def forward(ctx, xz, conv_w, conv_b, x_proj_w, dt_proj_w, dt_bias, A_log, D, grad_mode: bool):
+        dev = _require_cuda(xz, conv_w, conv_b, x_proj_w, dt_proj_w, dt_bias, A_log, D)
+        B, L, ED2 = xz.shape
+        ED, N = A_log.shape
+        K = conv_w.shape[-1]
+        R = dt_proj_w.shape[1]
+        dt = xz.dtype
+        if ED2 != 2 * ED or tuple(x_proj_w.shape) != (R + 2 * N, ED) or tuple(dt_proj_w.shape) != (ED, R) or dt not in _DT:
+            raise ValueError("mamba_inner: inconsistent shapes / dtype")
+        xz_ = _rows(xz.detach())
+        xin, z = xz_[..., :ED], xz_[..., ED:]
+        cw = conv_w.detach().float().reshape(ED, K).contiguous()
+        cb = _f32(conv_b)
+        Wx, Wdt = x_proj_w.detach().to(dt), dt_proj_w.detach().to(dt)
+        A_log_, D_, bias_ = _f32(A_log), _f32(D), _f32(dt_bias)
+        need_grad = grad_mode and any(ctx.needs_input_grad)
+        l = nat.lib()
+        u = torch.empty((B, L, ED), dtype=dt, device=dev)
+        out = torch.empty((B, L, ED), dtype=dt, device=dev)
+        with torch.cuda.device(dev):
+            nat.check(l.gfe_conv1d_silu_fwd(_ptr(xin), xin.stride(0), xin.stride(1), _ptr(cw), _ptr(cb), _ptr(u), u.stride(0),
+                                            u.stride(1), B, L, ED, K, _DT[dt], _stream(dev)), "conv1d_silu_fwd")
+            dbc = torch.mm(u.view(B * L, ED), Wx.t())                 # (B L, R + 2N): delta_low | B | C
+            delta = torch.mm(dbc[:, :R], Wdt.t()).view(B, L, ED)      # dt_proj without its bias (added inside the scan)
+            dbc3 = dbc.view(B, L, R + 2 * N)
+            Bm, Cm = dbc3[..., R:R + N], dbc3[..., R + N:]
+            a = nat.SelscanArgs()
+            _fill_common(a, u, delta, z, Bm, Cm, A_log_, D_, bias_, True)
+            a.out, a.out_bs, a.out_rs = out.data_ptr(), out.stride(0), out.stride(1)
+            sz = _sizes(B, L, ED, N, dev, _DT[dt])
+            nck = sz[0] if need_grad else 0
+            ckpt = _bytes(nck, dev)
+            ws = _bytes(sz[1], dev)
+            a.ckpt, a.ckpt_bytes = (0 if ckpt is None else ckpt.data_ptr()), nck
+            a.ws, a.ws_bytes = (0 if ws is None else ws.data_ptr()), sz[1]
+            nat.check(l.gfe_selscan_fwd(ctypes.byref(a), _stream(dev)), "selscan_fwd")
+        if need_grad:
+            ctx.save_for_backward(xz_, cw, cb, x_proj_w, dt_proj_w, A_log_, D_, bias_, u, dbc, delta, ckpt)
+            ctx.meta = (conv_w.shape, conv_w.dtype, None if conv_b is None else conv_b.dtype, x_proj_w.dtype, dt_proj_w.dtype,
+                        None if dt_bias is None else dt_bias.dtype, A_log.dtype, D.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xz_, cw, cb, x_proj_w, dt_proj_w, A_log_, D_, bias_, u, dbc, delta, ckpt = ctx.saved_tensors
+        dev = xz_.device
+        B, L, ED2 = xz_.shape
+        ED, N = A_log_.shape
+        K = cw.shape[1]
+        R = dt_proj_w.shape[1]
+        dt = xz_.dtype
+        dout = _as(dout, dt)
+        xin, z = xz_[..., :ED], xz_[..., ED:]
+        Wx, Wdt = x_proj_w.detach().to(dt), dt_proj_w.detach().to(dt)
+        dxz = torch.empty((B, L, 2 * ED), dtype=dt, device=dev)
+        dxin, dz = dxz[..., :ED], dxz[..., ED:]
+        ddbc = torch.empty((B * L, R + 2 * N), dtype=dt, device=dev)
+        ddbc3 = ddbc.view(B, L, R + 2 * N)
+        dBm, dCm = ddbc3[..., R:R + N], ddbc3[..., R + N:]
+        du = torch.empty((B, L, ED), dtype=dt, device=dev)
+        ddelta = torch.empty((B, L, ED), dtype=dt, device=dev)
+        dA_log = torch.empty((ED, N), dtype=torch.float32, device=dev)
+        dD = torch.empty((ED,), dtype=torch.float32, device=dev)
+        dbias = None if bias_ is None else torch.empty((ED,), dtype=torch.float32, device=dev)
+        dcw = torch.empty((ED, K), dtype=torch.float32, device=dev)
+        dcb = None if cb is None else torch.empty((ED,), dtype=torch.float32, device=dev)
+        dbc3 = dbc.view(B, L, R + 2 * N)
+        l = nat.lib()
+        with torch.cuda.device(dev):
+            a = nat.SelscanArgs()
+            _fill_common(a, u, delta, z, dbc3[..., R:R + N], dbc3[..., R + N:], A_log_, D_, bias_, True)
+            a.ckpt, a.ckpt_bytes = ckpt.data_ptr(), ckpt.numel()
+            a.dout, a.dout_bs, a.dout_rs = dout.data_ptr(), dout.stride(0), dout.stride(1)
+            a.du, a.du_bs, a.du_rs = du.data_ptr(), du.stride(0), du.stride(1)
+            a.ddelta, a.ddelta_bs, a.ddelta_rs = ddelta.data_ptr(), ddelta.stride(0), ddelta.stride(1)
+            a.dz, a.dz_bs, a.dz_rs = dz.data_ptr(), dz.stride(0), dz.stride(1)
+            a.dBm, a.dB_bs, a.dB_rs = dBm.data_ptr(), dBm.stride(0), dBm.stride(1)
+            a.dCm, a.dC_bs, a.dC_rs = dCm.data_ptr(), dCm.stride(0), dCm.stride(1)
+            a.dA_log, a.dD = dA_log.data_ptr(), dD.data_ptr()
+            a.ddt_bias = 0 if dbias is None else dbias.data_ptr()
+            nws = _sizes(B, L, ED, N, dev, _DT[dt])[2]
+            ws = _bytes(nws, dev)
+            a.ws, a.ws_bytes = (0 if ws is None else ws.data_ptr()), nws
+            nat.check(l.gfe_selscan_bwd(ctypes.byref(a), _stream(dev)), "selscan_bwd")
+            # dt_proj: d delta_low into its slice of d(dbc); weight gradient
+            dd2 = ddelta.view(B * L, ED)
+            ddbc[:, :R] = torch.mm(dd2, Wdt)
+            dWdt = torch.mm(dd2.t(), dbc[:, :R])
+            # x_proj: its input gradient lands on top of the scan's du in the GEMM epilogue; weight gradient
+            du2 = du.view(B * L, ED)
+            du2.addmm_(ddbc, Wx)
+            dWx = torch.mm(ddbc.t(), u.view(B * L, ED))
+            # conv + SiLU: d(conv input) straight into the first half of d(xz)
+            nws = l.gfe_conv1d_bwd_workspace_bytes(B, L, ED, K)
+            ws = _bytes(nws, dev)
+            nat.check(l.gfe_conv1d_silu_bwd(_ptr(xin), xin.stride(0), xin.stride(1), _ptr(cw), _ptr(cb), _ptr(du), du.stride(0),
+                                            du.stride(1), _ptr(dxin), dxin.stride(0), dxin.stride(1), _ptr(dcw), _ptr(dcb),
+                                            B, L, ED, K, _DT[dt], _ptr(ws), nws, _stream(dev)), "conv1d_silu_bwd")
+        cw_shape, cw_dt, cb_dt, wx_dt, wdt_dt, bias_dt, alog_dt, d_dt = ctx.meta
+        return (dxz, dcw.reshape(cw_shape).to(cw_dt), None if dcb is None else dcb.to(cb_dt), dWx.to(wx_dt), dWdt.to(wdt_dt),
+                None if dbias is None else dbias.to(bias_dt), dA_log.to(alog_dt), dD.to(d_dt), None)
+
+
+def mamba_inner_fn(xz: torch.Tensor, conv_w: torch.Tensor, conv_b: Optional[torch.Tensor], x_proj_w: torch.Tensor,
+                   dt_proj_w: torch.Tensor, dt_bias: Optional[torch.Tensor], A_log: torch.Tensor, D: torch.Tensor) -> torch.Tensor:
+    """y (B, L, ED) = gate(scan(conv(xz[..., :ED]), ...), xz[..., ED:]) for d_state = 16, d_conv in 2..4; see _MambaInnerFn."""
+    return _MambaInnerFn.apply(xz, conv_w, conv_b, x_proj_w, dt_proj_w, dt_bias, A_log, D, torch.is_grad_enabled())
+
+
 # ----------------------------------------------------------------- residual add + RMSNorm
 class _AddRMSNormFn(torch.autograd.Function):
     """resid = x (+ a);  y = (resid * rsqrt(mean(resid^2) + eps)) * w -- the residual add of ResidualBlock.forward

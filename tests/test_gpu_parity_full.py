@@ -175,3 +175,37 @@ def test_no_checkpoint_allocation_under_no_grad():
     assert p_ng < 1.5 * act, (p_ng, act)             # the output plus a small workspace
     assert p_g > 3.0 * act, (p_g, act)               # output + fp32 checkpoints every 8 steps (2 x act) + saved y (1 x act)
     assert torch.equal(o1, o2.detach())
+
+
+# ------------------------------------------------------------------- one-node inner path
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 3e-2)])
+def test_inner_node_matches_op_by_op(dtype, tol):
+    """MambaBlock.forward through the single autograd node (conv -> x_proj -> dt_proj -> scan -> gate, gradients written in
+    place) against the op-by-op composition of the same kernels: output and every gradient."""
+    from gfe_mamba_b200 import MambaBlock, MambaConfig
+    torch.manual_seed(3)
+    cfg = MambaConfig(d_model=64, n_layers=1, d_state=16, expand_factor=2, d_conv=4)
+    blk = MambaBlock(cfg).cuda()
+    with torch.no_grad():   # trained-looking parameters: A_log and D off their initial values
+        blk.A_log.add_(0.1 * torch.randn_like(blk.A_log))
+        blk.D.add_(0.1 * torch.randn_like(blk.D))
+    x0 = torch.randn(3, 77, 64, device="cuda")
+    dy = torch.randn(3, 77, 64, device="cuda")
+
+    def run(fused):
+        blk.zero_grad(set_to_none=True)
+        if not fused:
+            blk._inner_fusable = lambda xz: False
+        elif "_inner_fusable" in blk.__dict__:
+            del blk.__dict__["_inner_fusable"]
+        x = x0.clone().requires_grad_()
+        with torch.autocast("cuda", dtype=dtype, enabled=dtype != torch.float32):
+            y = blk(x)
+        y.float().backward(dy)
+        return [y.detach().float(), x.grad.float()] + [p.grad.float().clone() for p in blk.parameters()]
+
+    a, b = run(True), run(False)
+    names = ["y", "dx"] + [n for n, _ in blk.named_parameters()]
+    for n, ga, gb in zip(names, a, b):
+        err = float((ga - gb).abs().max() / gb.abs().max().clamp_min(1e-30))
+        assert err < tol, (n, err)
