@@ -184,9 +184,7 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
                     for (int q = 0; q < CKP; ++q) {   // piece tid + q NT of [half][c][16]
                         constexpr int QH = PH / NT;    // pieces per thread and half
                         if (q / QH < nhalf) cp_async<16>(dst_ck + so + q * NT * 16, sck + (size_t)(q / QH) * ck_step + (q % QH) * NT * 16);
-#if GFE_CBWD_FUSED
                         else *reinterpret_cast<float4 *>(smem + so + SM::kOffCk + (tid + q * NT) * 16) = make_float4(0.f, 0.f, 0.f, 0.f);   // identity half
-#endif
                     }
                     sck -= 2 * ck_step;
                 }
@@ -358,148 +356,6 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
             __syncthreads();   // (1) slots of this chunk are complete
             GFE_CLK(1);
 
-#if !GFE_CBWD_FUSED
-#pragma unroll 1
-            for (int half = 1; half >= 0; --half) {   // steps 8..15, then 0..7 (one copy of the sweep code)
-                const int jo = half * kCkptV2;
-                if (tb + jo >= t1) continue;          // block-uniform: the half lies beyond the sequence
-                // ------------------------------------------------------------ phase B
-                const float4 *dd_p = dd_r + jo * NP;
-                const float2 *dy_p = dy_r + jo * NP;
-                const float4 *bc_p = bc_r + jo * 8;
-                float *red_p = red_w + jo * kCRedRow;
-                float2 h0[2][kCkptV2 + 1], h1[2][kCkptV2 + 1];
-#if GFE_CBWD_KEEP_A
-                float2 e0h[2][kCkptV2], e1h[2][kCkptV2];
-#endif
-#pragma unroll
-                for (int ch = 0; ch < 2; ++ch) {
-                    const float4 ck = ckpt_load_smem(reinterpret_cast<const CK *>(smem + stage * SM::kStage + SM::kOffCk + half * SM::kCk) +
-                                                     (2 * rp + ch) * kNState + 4 * rq);
-                    h0[ch][0] = sw ? make_float2(ck.y, ck.x) : make_float2(ck.x, ck.y);
-                    h1[ch][0] = sw ? make_float2(ck.w, ck.z) : make_float2(ck.z, ck.w);
-                }
-#pragma unroll
-                for (int j = 0; j < kCkptV2; ++j) {   // forward sweep: re-derive the states of this half chunk
-                    const float4 dd = dd_p[j * NP];   // {dl0, dl0 u0, dl1, dl1 u1}
-                    const float4 B4 = bc_p[j * 8];
-                    const float2 B01 = make_float2(B4.x, B4.y), B23 = make_float2(B4.z, B4.w);
-#pragma unroll
-                    for (int ch = 0; ch < 2; ++ch) {
-                        const float2 dl2 = splat2(ch ? dd.y : dd.x), du2 = splat2(ch ? dd.w : dd.z);   // scalar-broadcast operands
-                        const float2 e0 = ex2_2(fmul2(dl2, A2[ch][0])), e1 = ex2_2(fmul2(dl2, A2[ch][1]));
-#if GFE_CBWD_KEEP_A
-                        e0h[ch][j] = e0; e1h[ch][j] = e1;
-#endif
-                        h0[ch][j + 1] = ffma2(e0, h0[ch][j], fmul2(du2, B01));
-                        h1[ch][j + 1] = ffma2(e1, h1[ch][j], fmul2(du2, B23));
-                    }
-                }
-                // slot loads of step j - 1 are issued before the stores of step j: neither nvcc nor ptxas moves an LDS above
-                // a (may-alias) STS, so in plain source order every step would wait out a full LDS latency
-                float4 dd_n = dd_p[(kCkptV2 - 1) * NP], B_n = bc_p[(kCkptV2 - 1) * 8], C_n = bc_p[(kCkptV2 - 1) * 8 + 4];
-                float2 dy_n = dy_p[(kCkptV2 - 1) * NP];
-#pragma unroll
-                for (int jb = kCkptV2 - 2; jb >= 0; jb -= 2) {
-                    float v[16];   // [kind (dB, dC)][step in group (2)][state in quad (4)], summed over the lane's two channels
-#pragma unroll
-                    for (int jj = 1; jj >= 0; --jj) {
-                        const int j = jb + jj;
-                        const float4 dd = dd_n, B4 = B_n, C4 = C_n;
-                        const float2 dyv = dy_n;
-                        if (j > 0) {
-                            dd_n = dd_p[(j - 1) * NP]; B_n = bc_p[(j - 1) * 8]; C_n = bc_p[(j - 1) * 8 + 4];
-                            dy_n = dy_p[(j - 1) * NP];
-                        }
-                        const float2 B01 = make_float2(B4.x, B4.y), B23 = make_float2(B4.z, B4.w);
-                        const float2 C01 = make_float2(C4.x, C4.y), C23 = make_float2(C4.z, C4.w);
-                        float2 dc0, dc1, db0, db1;
-                        float4 part;
-#pragma unroll
-                        for (int ch = 0; ch < 2; ++ch) {
-                            const float2 dl2 = splat2(ch ? dd.y : dd.x), du2 = splat2(ch ? dd.w : dd.z), dy2 = splat2(ch ? dyv.y : dyv.x);
-                            const float2 gg0 = ffma2(C01, dy2, G[ch][0]);   // g[t] = C dy + a[t+1] g[t+1]
-                            const float2 gg1 = ffma2(C23, dy2, G[ch][1]);
-                            if (ch == 0) {
-                                dc0 = fmul2(dy2, h0[ch][j + 1]); dc1 = fmul2(dy2, h1[ch][j + 1]);   // dC_t[n] += dy h[t]
-                                db0 = fmul2(gg0, du2); db1 = fmul2(gg1, du2);                       // dB_t[n] += g delta u
-                            } else {
-                                dc0 = ffma2(dy2, h0[ch][j + 1], dc0); dc1 = ffma2(dy2, h1[ch][j + 1], dc1);
-                                db0 = ffma2(gg0, du2, db0); db1 = ffma2(gg1, du2, db1);
-                            }
-                            const float2 sb = ffma2(gg1, B23, fmul2(gg0, B01));                      // sum_n g B
-#if GFE_CBWD_KEEP_A
-                            G[ch][0] = fmul2(e0h[ch][j], gg0);                                       // a[t] g[t]
-                            G[ch][1] = fmul2(e1h[ch][j], gg1);
-#else                       // the decay factors are re-derived instead of living in 64 registers
-                            G[ch][0] = fmul2(ex2_2(fmul2(dl2, A2[ch][0])), gg0);                     // a[t] g[t]
-                            G[ch][1] = fmul2(ex2_2(fmul2(dl2, A2[ch][1])), gg1);
-#endif
-                            const float2 w0 = fmul2(G[ch][0], h0[ch][j]), w1 = fmul2(G[ch][1], h1[ch][j]);   // (d a) a = g a h[t-1]
-                            const float2 sa = ffma2(w1, A2[ch][1], fmul2(w0, A2[ch][0]));            // sum_n (da a) A log2e
-                            dA[ch][0] = ffma2(w0, dl2, dA[ch][0]);                                   // dA[c,n] += (da a) delta
-                            dA[ch][1] = ffma2(w1, dl2, dA[ch][1]);
-                            if (ch == 0) { part.x = sb.x + sb.y; part.z = sa.x + sa.y; }   // {S1_0, S1_1, S2_0, S2_1}
-                            else { part.y = sb.x + sb.y; part.w = sa.x + sa.y; }
-                        }
-                        s_w[j * (4 * SPL)] = part;
-                        v[4 * jj] = db0.x; v[4 * jj + 1] = db0.y; v[4 * jj + 2] = db1.x; v[4 * jj + 3] = db1.y;
-                        v[8 + 4 * jj] = dc0.x; v[8 + 4 * jj + 1] = dc0.y; v[8 + 4 * jj + 2] = dc1.x; v[8 + 4 * jj + 3] = dc1.y;
-                    }
-                    // reduce the 16 values over the 8 lanes that share this quad (lane bits 2, 3, 4)
-                    float r1[8];   // [kind][jj][m]: state 4 rq + 2 m + sw (odd pairs hold their state pairs swapped)
-#pragma unroll
-                    for (int m = 0; m < 8; ++m) r1[m] = v[2 * m] + __shfl_xor_sync(0xffffffffu, v[2 * m + 1], 4);
-                    float r2[4];   // [kind][jj]: exchange on m
-#pragma unroll
-                    for (int m = 0; m < 4; ++m) {
-                        const float keep = up8 ? r1[2 * m + 1] : r1[2 * m];
-                        const float send = up8 ? r1[2 * m] : r1[2 * m + 1];
-                        r2[m] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-                    }
-                    float r3[2];   // [kind]: exchange on jj
-#pragma unroll
-                    for (int m = 0; m < 2; ++m) {
-                        const float keep = up16 ? r2[2 * m + 1] : r2[2 * m];
-                        const float send = up16 ? r2[2 * m] : r2[2 * m + 1];
-                        r3[m] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                    }
-                    *reinterpret_cast<float2 *>(red_p + jb * kCRedRow) = make_float2(r3[0], r3[1]);   // {dB, dC} of (step, state)
-                }
-
-                // ------------------------------------------------------------ phase C (this warp's 8 pairs x 8 steps)
-                GFE_CLK(2);
-                __syncwarp();
-                {
-                    T *dup = dub + ((int64_t)tb + jo + cr) * p.du_rs, *ddp = ddb + ((int64_t)tb + jo + cr) * p.dd_rs;
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        const int tl = cr + 4 * q, t = jo + tl;
-                        if (tb + t < t1) {
-                            const float4 *sp4 = sS + (tl * 4) * SPL + cp;   // {S1_0, S1_1, S2_0, S2_1}, one plane per quad
-                            const float4 p0 = sp4[0], p1 = sp4[SPL], p2 = sp4[2 * SPL], p3 = sp4[3 * SPL];
-                            const float4 dd = sDD[t * NP + cp];
-                            const float2 dy = sDY[t * NP + cp];
-                            const float4 e4 = sEpi[t * NP + cp];
-                            const float2 s1 = fadd2(fadd2(make_float2(p0.x, p0.y), make_float2(p1.x, p1.y)), fadd2(make_float2(p2.x, p2.y), make_float2(p3.x, p3.y)));
-                            const float2 s2 = fmul2(fadd2(fadd2(make_float2(p0.z, p0.w), make_float2(p1.z, p1.w)), fadd2(make_float2(p2.z, p2.w), make_float2(p3.z, p3.w))), splat2(kLn2));
-                            const float2 u2 = make_float2(e4.x, e4.y);
-                            const float2 draw = fmul2(ffma2(s1, u2, s2), make_float2(e4.z, e4.w));   // d delta through softplus
-                            const float2 du = ffma2(make_float2(dd.x, dd.y), s1, fmul2(Dc, dy));
-                            stg_pair<T>(dup, du.x, du.y, vec);
-                            stg_pair<T>(ddp, draw.x, draw.y, vec);
-                            dD_acc = ffma2(dy, u2, dD_acc);
-                            dbias_acc = fadd2(dbias_acc, draw);
-                        }
-                        dup += 4 * p.du_rs;
-                        ddp += 4 * p.dd_rs;
-                    }
-                }
-                __syncwarp();   // the next half overwrites the partial planes
-                GFE_CLK(6);
-            }
-
-#else
             // ------------------------------------------------------------ phase B + C
             // Both halves of the chunk are always walked (a half beyond the sequence consists of identity steps: delta = 0,
             // dy = 0, a zeroed checkpoint).  The reverse sweep of steps 8..15 and the forward sweep of steps 0..7 are
@@ -650,7 +506,6 @@ __global__ void __launch_bounds__(2 * CPC, GFE_CBWD_MINB * (64 / CPC)) selscan_b
             phase_c(0);
             GFE_CLK(6);
 
-#endif
             cp_async_wait<NST - 2>();
             __syncthreads();   // (2) per-warp dB|dC rows complete; next chunk visible; this chunk's stage free
             GFE_CLK(3);

@@ -327,12 +327,6 @@ static int persistent_grid(int nt, size_t smem, int total) {
 #ifndef GFE_BWD_CPC_DEFAULT
 #define GFE_BWD_CPC_DEFAULT 64
 #endif
-#ifndef GFE_CBWD_KEEP_A
-#define GFE_CBWD_KEEP_A 1      // backward: 1 = the decay factors of a half chunk stay in registers (64 more) instead of being re-derived
-#endif
-#ifndef GFE_CBWD_FUSED
-#define GFE_CBWD_FUSED 0       // backward: 1 = reverse sweep of steps 8..15 interleaved with the forward sweep of steps 0..7
-#endif
 #ifndef GFE_CBWD_MINB
 #define GFE_CBWD_MINB 2        // backward: CTAs of 128 threads per SM the register budget is set for (2: 255 registers, 3: 168)
 #endif
