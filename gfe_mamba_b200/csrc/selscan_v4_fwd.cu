@@ -26,7 +26,7 @@ namespace gfe {
 #define GFE_SOFTPLUS2 1
 #endif
 #ifndef GFE_V4_PREFETCH
-#define GFE_V4_PREFETCH 1
+#define GFE_V4_PREFETCH 2
 #endif
 #ifndef GFE_V4_POLY
 #define GFE_V4_POLY 1
