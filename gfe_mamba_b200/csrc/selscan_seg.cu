@@ -9,20 +9,24 @@
 //      chained kernels (two channels x four states per lane, item mapping through shared slots), plus sum(delta) of the
 //      segment.  No C.h, no outputs, no checkpoints, no cross-lane reduction: 2 packed FP32 ops and 2 exp2 per state pair
 //      and step; one exp2 pair of four runs as a polynomial on the FMA pipe, because this loop is MUFU-bound.
-//   2. combine pass: carry[s + 1] = exp2(A sum_delta[s]) carry[s] + local[s], one thread per (b, c, n), 8 loads in flight.
+//   2. combine pass: carry[s + 1] = exp2(A sum_delta[s]) carry[s] + local[s] over the segments, as a two-level scan (32 runs of
+//      up to 8 segments per (b, c, n) element, chained through shared memory).
 //   3. main pass: the chained kernels with ChainSched::independent = 1 (selscan_v4_fwd.cu, selscan_chain_bwd.cu).
 #include "common.cuh"
 #include "selscan_shared.cuh"
 
 namespace gfe {
 
+#ifndef GFE_SEG_STAGES
+#define GFE_SEG_STAGES 3
+#endif
 #ifndef GFE_SEG_POLY
 #define GFE_SEG_POLY 1   // exp2 pairs (of 4 per lane and step) evaluated on the FMA pipe
 #endif
 
 template <typename T, bool HAS_Z, int CPC>
 struct SegSumSmem {
-    static constexpr int kStages = sizeof(T) == 4 ? 2 : 3;
+    static constexpr int kStages = GFE_SEG_STAGES;                       // (2, 3 and 4 stages measure the same)
     static constexpr int kNTile = HAS_Z ? 3 : 2;                         // x (u forward | dout reverse), delta, [z]
     static constexpr int kTile = kChunk * CPC * (int)sizeof(T);
     static constexpr int kBCRaw = kChunk * kNState * (int)sizeof(T);     // B rows (forward) | C rows (reverse)
@@ -215,32 +219,85 @@ __global__ void __launch_bounds__(2 * CPC, 4 * (64 / CPC)) selscan_seg_summary_k
 
 // carry[slot] <- exp2(A sum_delta[slot]) carry[previous slot] + local[slot], in place; forward: slots ascending (the result is
 // the carry-in of segment slot + 1), reverse: slots descending (the reverse carry-in of segment slot).
-__global__ void __launch_bounds__(256) selscan_seg_combine_kernel(float *__restrict__ segc, const float *__restrict__ segsd,
-                                                                  const float *__restrict__ A_log, int nslots, int B, int ED, int rev) {
+// A CTA of 32 x 32 threads serves 32 consecutive (b, c, n) elements: thread (x, y) owns element x and the y-th run of K <= 8
+// consecutive slots (in processing order).  It loads its run (all loads in flight at once), reduces it to one (P, S) pair,
+// row y = 0 chains the 32 pairs through shared memory, and every thread replays its run from the carry it was handed.
+constexpr int kCombK = (kMaxSeg + 31) / 32;
+__global__ void __launch_bounds__(1024) selscan_seg_combine_kernel(float *__restrict__ segc, const float *__restrict__ segsd,
+                                                                   const float *__restrict__ A_log, int nslots, int B, int ED, int rev) {
+    __shared__ float sP[32][33], sS[32][33];
+    const int x = threadIdx.x, y = threadIdx.y;
+    const int64_t n_el = (int64_t)B * ED * kNState;
+    const int64_t idx = (int64_t)blockIdx.x * 32 + x;
+    const bool act = idx < n_el;
+    const int64_t ic = act ? idx : n_el - 1;
+    const int64_t bc = ic >> 4;
+    const float a2 = -expf(__ldg(A_log + (size_t)(bc % ED) * kNState + (ic & 15))) * kLog2e;
+    const int K = (nslots + 31) / 32;          // slots per run (<= kCombK)
+    const int s0 = y * K;
+    float S[kCombK], Pd[kCombK];
+#pragma unroll
+    for (int u = 0; u < kCombK; ++u) {
+        const int s = s0 + u;
+        S[u] = 0.f; Pd[u] = 1.f;
+        if (u < K && s < nslots) {
+            const int64_t slot = rev ? nslots - 1 - s : s;
+            S[u] = __ldcg(segc + slot * n_el + ic);
+            Pd[u] = ex2_approx(a2 * __ldcg(segsd + slot * (n_el >> 4) + bc));
+        }
+    }
+    float P = 1.f, H = 0.f;                    // the run as one step: H_out = P H_in + H
+#pragma unroll
+    for (int u = 0; u < kCombK; ++u) { H = fmaf(Pd[u], H, S[u]); P *= Pd[u]; }
+    sP[y][x] = P; sS[y][x] = H;
+    __syncthreads();
+    if (y == 0) {
+        float h = 0.f;
+        for (int r = 0; r < 32; ++r) {          // carry INTO run r
+            const float pr = sP[r][x], sr = sS[r][x];
+            sS[r][x] = h;
+            h = fmaf(pr, h, sr);
+        }
+    }
+    __syncthreads();
+    H = sS[y][x];
+    if (act) {
+#pragma unroll
+        for (int u = 0; u < kCombK; ++u) {
+            const int s = s0 + u;
+            if (u < K && s < nslots) {
+                const int64_t slot = rev ? nslots - 1 - s : s;
+                H = fmaf(Pd[u], H, S[u]);
+                segc[slot * n_el + ic] = H;
+            }
+        }
+    }
+}
+
+// The same for a few segments (<= 32, e.g. the production shape): one thread per element walks the slots, 8 loads in flight.
+__global__ void __launch_bounds__(256) selscan_seg_combine_seq_kernel(float *__restrict__ segc, const float *__restrict__ segsd,
+                                                                      const float *__restrict__ A_log, int nslots, int B, int ED, int rev) {
     const int64_t n_el = (int64_t)B * ED * kNState;
     const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (idx >= n_el) return;
     const int64_t bc = idx >> 4;
-    const int c = (int)(bc % ED);
-    const float a2 = -expf(__ldg(A_log + (size_t)c * kNState + (idx & 15))) * kLog2e;
+    const float a2 = -expf(__ldg(A_log + (size_t)(bc % ED) * kNState + (idx & 15))) * kLog2e;
     float H = 0.f;
     constexpr int U = 8;
     for (int s0 = 0; s0 < nslots; s0 += U) {
         float S[U], sd[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int s = s0 + u;
-            if (s < nslots) {
-                const int64_t slot = rev ? nslots - 1 - s : s;
+            if (s0 + u < nslots) {
+                const int64_t slot = rev ? nslots - 1 - (s0 + u) : s0 + u;
                 S[u] = __ldcg(segc + slot * n_el + idx);
                 sd[u] = __ldcg(segsd + slot * (n_el >> 4) + bc);
             }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int s = s0 + u;
-            if (s < nslots) {
-                const int64_t slot = rev ? nslots - 1 - s : s;
+            if (s0 + u < nslots) {
+                const int64_t slot = rev ? nslots - 1 - (s0 + u) : s0 + u;
                 H = fmaf(ex2_approx(a2 * sd[u]), H, S[u]);
                 segc[slot * n_el + idx] = H;
             }
@@ -293,7 +350,10 @@ int seg_launch_carries(const ScanParams &p, const ChainSched &cs, int dtype, int
     int rc = check_launch(rev ? "selscan_bwd segment summary" : "selscan_fwd segment summary");
     if (rc != GFE_OK) return rc;
     const int64_t n_el = (int64_t)p.B * p.ED * kNState;
-    selscan_seg_combine_kernel<<<(unsigned)ceil_div64(n_el, 256), 256, 0, st>>>(cs.segc, cs.segsd, p.A_log, cs.nseg - 1, p.B, p.ED, rev ? 1 : 0);
+    if (cs.nseg - 1 <= 32)
+        selscan_seg_combine_seq_kernel<<<(unsigned)ceil_div64(n_el, 256), 256, 0, st>>>(cs.segc, cs.segsd, p.A_log, cs.nseg - 1, p.B, p.ED, rev ? 1 : 0);
+    else
+        selscan_seg_combine_kernel<<<(unsigned)ceil_div64(n_el, 32), dim3(32, 32), 0, st>>>(cs.segc, cs.segsd, p.A_log, cs.nseg - 1, p.B, p.ED, rev ? 1 : 0);
     return check_launch("selscan segment combine");
 }
 
