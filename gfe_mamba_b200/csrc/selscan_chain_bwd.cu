@@ -8,17 +8,20 @@
 // shuffle reduction runs over half as many values, and the per-(t, channel) sums over states leave the lane as ONE
 // 16-byte store.  Per lane and step (8 state-steps): 6 LDS + 48 packed FP32 + 16 exp2 + 7 SHFL + 1 STS.128.
 //
-// Per unit = (L-segment, batch row, channel block), segments walked last to first (ChainSched, see selscan_shared.cuh):
-//   chunks of 16 steps are staged by cp.async (u, delta, dout, [y, z], B, C) and walked in reverse:
-//   phase A  (item mapping, thread per (t, channel pair)): softplus and its derivative, dy = dout * silu(z), dz, the
-//            slots {dl0, dl0 u0, dl1, dl1 u1}, {dy0, dy1}, {u0, sg0, u1, sg1}; B|C rows -> fp32 quads (natural and
-//            pair-swapped plane);
-//   phase B  (recurrence mapping), per half chunk of 8 steps: a forward sweep re-derives the 8 states from the half's
-//            checkpoint into registers; the reverse sweep runs g[t] = C dy + a[t+1] g[t+1] and forms every contraction
-//            with packed FP32 ops; dB|dC are reduced over the 8 pairs of the warp in groups of 2 steps (14 SHFL per 16
-//            values; the first level needs no selects because odd pairs hold their state pairs swapped);
-//   phase C  (warp-local item mapping, right after each half: only __syncwarp): du, ddelta from the four quads'
-//            partials; dD / ddt_bias accumulation;
+// Per unit = (L-segment, batch row, channel block), segments walked last to first (ChainSched, see selscan_shared.cuh; the
+// segments are either chained through flags or independent, their carries then coming from selscan_seg.cu):
+//   chunks of 16 steps are staged by cp.async (u, delta, dout, [y, z], B, C and the two checkpoints) and walked in reverse:
+//   phase A  (item mapping, thread per (t, channel pair), packed FP32 over the pair): softplus and its derivative,
+//            dy = dout * silu(z), dz, the slots {dl0, dl1, dl0 u0, dl1 u1}, {dy0, dy1}, {u0, u1, sg0, sg1}; B|C rows -> fp32
+//            quads (natural and pair-swapped plane).  Rows are masked only in a ragged last chunk (template flag);
+//   phase B  (recurrence mapping): a forward sweep re-derives the 8 states and decay factors of steps 8..15 from their
+//            checkpoint into registers; then the reverse sweep of steps 8..15 (g[t] = C dy + a[t+1] g[t+1], every
+//            contraction as packed FP32 ops; dB|dC reduced over the 8 pairs of the warp in groups of 2 steps: 14 SHFL per 16
+//            values, the first level without selects because odd pairs hold their state pairs swapped) runs INTERLEAVED
+//            with the forward sweep of steps 0..7 -- one is bound by FP32 operand delivery, the other by MUFU, and the
+//            histories hand their registers over step by step -- followed by the reverse sweep of steps 0..7;
+//   phase C  (warp-local item mapping, right after each reverse sweep: only __syncwarp, packed FP32): du, ddelta from the
+//            four quads' partials; dD / ddt_bias accumulation;
 //   then the warps' dB|dC rows are added and leave as one row per (CTA, t) for selscan_bwd_finalize_bc.
 #include <type_traits>
 

@@ -1,5 +1,5 @@
 // selscan_shared.cuh -- parameter block and device helpers shared by every selective-scan kernel
-// (generic kernels in selscan.cu, L-split "fast" kernels in selscan_fast.cuh, chained v2 kernels in selscan_v2_*.cu).
+// (chained kernels in selscan_v4_fwd.cu / selscan_chain_bwd.cu, their segment summaries in selscan_seg.cu, generic kernels in selscan.cu).
 #pragma once
 
 #include "common.cuh"

@@ -9,9 +9,11 @@
 //     scalar operand of FFMA2/FMUL2 into the R.F32 broadcast form);
 //   * a CTA of 128 threads serves 64 channels; every thread stages exactly one 16-byte piece per tile with offsets
 //     computed once per unit, and the per-(t, channel pair) scalar work runs once per pair in the item mapping;
-//   * per lane and step: 3 LDS.128 + 16 packed FP32 ops + 8 exp2 (2 of them on the FMA pipe) + 1 STS.64 for 8
-//     state-steps (v2: 3 LDS.128 + 8 + 4 + 1 for 4).
-// Segment chaining (ChainSched); checkpoints [b][t/8][c][16] (fp32, bf16 for bf16 activations) and the saved y are what
+//   * per lane and step: 3 LDS.128 + 16 packed FP32 ops + 8 exp2 (every other step 2 of them on the FMA pipe) + 1 STS.64 for 8
+//     state-steps (v2: 3 LDS.128 + 8 + 4 + 1 for 4); the slot loads run two steps ahead of their use;
+//   * the item phases work on packed FP32 over the channel pair, slots are laid out in pair order {dl0, dl1, dl0 u0, dl1 u1},
+//     rows are masked only in a ragged last chunk, paired stores are a compile-time property of the cp.async instantiation.
+// Segments are chained (ChainSched) or independent (carries from selscan_seg.cu); checkpoints [b][t/8][c][16] (fp32, bf16 for bf16 activations) and the saved y are what
 // selscan_chain_bwd.cu consumes.
 #include <type_traits>
 

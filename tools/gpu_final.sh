@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round artifacts in ONE gpurun call: parity tests, smoke, every bench line + reference arm, ncu launch list, full captures of the
 # two scan kernels (-> traffic), per-kernel roofline benches, training-step lines.   gpurun --timeout 2400 -- 'bash tools/gpu_final.sh tag'
-TAG=${1:-r02}; OUT=gpurun_out/$TAG; mkdir -p $OUT
+TAG=${1:-r02b}; OUT=gpurun_out/$TAG; mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/gpu.txt 2>&1
 timeout 900 python -m pytest tests -m gpu -q > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_gpu.log; tail -3 $OUT/pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; tail -2 $OUT/smoke.log
