@@ -8,6 +8,8 @@
 //   forward : read xin, write u                      (2 * ED * s bytes / token)
 //   backward: read xin, du, write dxin               (3 * ED * s bytes / token), dw/dbias via
 //             per-(b, tile) partial sums + a deterministic finalize kernel.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace gfe {
@@ -201,6 +203,207 @@ __global__ void __launch_bounds__(128) conv1d_silu_bwd_kernel(ConvParams p) {
     }
 }
 
+// ---- packed variants: NP channel PAIRS per lane (2 for 16-bit activations, 1 for fp32), every FP32 op on a float2 ----------
+// The scalar kernels above spend ~25 instructions per element in 16-bit (unpack, per-channel FFMA chains, 64-bit address
+// arithmetic per row): issue-bound at a third of the HBM peak.  Here the window, the weights and every product are float2 over
+// a channel pair, rows are addressed through running pointers, and full groups of 8 rows run without row checks.
+template <typename T, int NP> struct PairVec;
+template <> struct PairVec<float, 1> {
+    using Raw = float2;
+    static __device__ __forceinline__ void unpack(Raw r, float2 (&v)[1]) { v[0] = r; }
+    static __device__ __forceinline__ Raw pack(const float2 (&v)[1]) { return v[0]; }
+};
+template <> struct PairVec<__nv_bfloat16, 2> {
+    using Raw = uint2;
+    static __device__ __forceinline__ void unpack(Raw r, float2 (&v)[2]) {
+        v[0] = make_float2(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u));
+        v[1] = make_float2(__uint_as_float(r.y << 16), __uint_as_float(r.y & 0xffff0000u));
+    }
+    static __device__ __forceinline__ Raw pack(const float2 (&v)[2]) {
+        const __nv_bfloat162 a = __floats2bfloat162_rn(v[0].x, v[0].y), b = __floats2bfloat162_rn(v[1].x, v[1].y);
+        return make_uint2(*reinterpret_cast<const uint32_t *>(&a), *reinterpret_cast<const uint32_t *>(&b));
+    }
+};
+template <> struct PairVec<__half, 2> {
+    using Raw = uint2;
+    static __device__ __forceinline__ void unpack(Raw r, float2 (&v)[2]) {
+        v[0] = __half22float2(*reinterpret_cast<const __half2 *>(&r.x));
+        v[1] = __half22float2(*reinterpret_cast<const __half2 *>(&r.y));
+    }
+    static __device__ __forceinline__ Raw pack(const float2 (&v)[2]) {
+        const __half2 a = __floats2half2_rn(v[0].x, v[0].y), b = __floats2half2_rn(v[1].x, v[1].y);
+        return make_uint2(*reinterpret_cast<const uint32_t *>(&a), *reinterpret_cast<const uint32_t *>(&b));
+    }
+};
+__device__ __forceinline__ float2 sigmoid2(float2 v) {
+    const float2 den = fadd2(ex2_2(fmul2(v, splat2(-kLog2e))), splat2(1.0f));
+    return make_float2(rcp_approx(den.x), rcp_approx(den.y));
+}
+
+template <typename T, int K, int NP>
+__global__ void __launch_bounds__(128) conv1d_silu_fwd_pk_kernel(ConvParams p) {
+    using PV = PairVec<T, NP>;
+    using Raw = typename PV::Raw;
+    constexpr int V = 2 * NP;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) * V;
+    if (c >= p.ED) return;
+    const int tile = blockIdx.y, b = blockIdx.z;
+    const int t0 = tile * kConvTile, t1 = min(p.L, t0 + kConvTile);
+    const int64_t xs = p.x_rs * (int64_t)sizeof(T), us = p.u_rs * (int64_t)sizeof(T);
+    const char *xp = reinterpret_cast<const char *>(reinterpret_cast<const T *>(p.xin) + (int64_t)b * p.x_bs + c) + (int64_t)t0 * xs;
+    char *up = reinterpret_cast<char *>(reinterpret_cast<T *>(p.u) + (int64_t)b * p.u_bs + c) + (int64_t)t0 * us;
+    float2 w[NP][K], bias[NP], win[NP][K];   // win[.][k] = xin[t - (K-1) + k]
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) w[i][k] = make_float2(__ldg(p.w + (size_t)(c + 2 * i) * K + k), __ldg(p.w + (size_t)(c + 2 * i + 1) * K + k));
+        bias[i] = p.bias ? make_float2(__ldg(p.bias + c + 2 * i), __ldg(p.bias + c + 2 * i + 1)) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < K - 1; ++k) {
+        const int t = t0 - (K - 1) + k;
+        float2 v[NP];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) v[i] = make_float2(0.f, 0.f);
+        if (t >= 0) PV::unpack(__ldcs(reinterpret_cast<const Raw *>(xp + (int64_t)(k - (K - 1)) * xs)), v);
+#pragma unroll
+        for (int i = 0; i < NP; ++i) win[i][k + 1] = v[i];
+    }
+    constexpr int U = 8;
+    auto group = [&](auto full_c, int nrows) {
+        constexpr bool FULL = decltype(full_c)::value;
+        Raw xr[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j)
+            if (FULL || j < nrows) xr[j] = __ldcs(reinterpret_cast<const Raw *>(xp + j * xs));
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            if (FULL || j < nrows) {
+                float2 v[NP], o[NP];
+                PV::unpack(xr[j], v);
+#pragma unroll
+                for (int i = 0; i < NP; ++i) {
+#pragma unroll
+                    for (int k = 0; k < K - 1; ++k) win[i][k] = win[i][k + 1];
+                    win[i][K - 1] = v[i];
+                    float2 acc = bias[i];
+#pragma unroll
+                    for (int k = 0; k < K; ++k) acc = ffma2(w[i][k], win[i][k], acc);
+                    o[i] = fmul2(acc, sigmoid2(acc));
+                }
+                __stcs(reinterpret_cast<Raw *>(up + j * us), PV::pack(o));
+            }
+        }
+        xp += U * xs;
+        up += U * us;
+    };
+    int tb = t0;
+    for (; tb + U <= t1; tb += U) group(std::true_type{}, U);
+    if (tb < t1) group(std::false_type{}, t1 - tb);
+}
+
+template <typename T, int K, int NP>
+__global__ void __launch_bounds__(128) conv1d_silu_bwd_pk_kernel(ConvParams p) {
+    using PV = PairVec<T, NP>;
+    using Raw = typename PV::Raw;
+    constexpr int V = 2 * NP;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) * V;
+    if (c >= p.ED) return;
+    const int tile = blockIdx.y, b = blockIdx.z;
+    const int t0 = tile * kConvTile, t1 = min(p.L, t0 + kConvTile);
+    const int64_t xs = p.x_rs * (int64_t)sizeof(T), gs = p.du_rs * (int64_t)sizeof(T), ds = p.dx_rs * (int64_t)sizeof(T);
+    const char *xp = reinterpret_cast<const char *>(reinterpret_cast<const T *>(p.xin) + (int64_t)b * p.x_bs + c) + (int64_t)t0 * xs;
+    const char *gp = reinterpret_cast<const char *>(reinterpret_cast<const T *>(p.du) + (int64_t)b * p.du_bs + c) + (int64_t)t0 * gs;
+    // dxin[s] is complete when dv[s + K - 1] is known: the row stored while step t is processed is t - (K - 1)
+    char *dp = reinterpret_cast<char *>(reinterpret_cast<T *>(p.dxin) + (int64_t)b * p.dx_bs + c) + (int64_t)(t0 - (K - 1)) * ds;
+    float2 w[NP][K], bias[NP], win[NP][K], dvw[NP][K], dw[NP][K], db[NP];   // dvw[.][k] = dv[t - (K-1) + k]
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            w[i][k] = make_float2(__ldg(p.w + (size_t)(c + 2 * i) * K + k), __ldg(p.w + (size_t)(c + 2 * i + 1) * K + k));
+            dvw[i][k] = dw[i][k] = make_float2(0.f, 0.f);
+        }
+        bias[i] = p.bias ? make_float2(__ldg(p.bias + c + 2 * i), __ldg(p.bias + c + 2 * i + 1)) : make_float2(0.f, 0.f);
+        db[i] = make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < K - 1; ++k) {
+        const int t = t0 - (K - 1) + k;
+        float2 v[NP];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) v[i] = make_float2(0.f, 0.f);
+        if (t >= 0) PV::unpack(__ldcs(reinterpret_cast<const Raw *>(xp + (int64_t)(k - (K - 1)) * xs)), v);
+#pragma unroll
+        for (int i = 0; i < NP; ++i) win[i][k + 1] = v[i];
+    }
+    // dv is needed K-1 steps past the tile to finish dxin of the tile's last steps
+    const int tend = t1 + (K - 1);
+    constexpr int U = 8;
+    // MAIN: every row of the group lies in [t0, t1) and its output row t - (K-1) >= t0 is checked per row only in the first group
+    auto group = [&](auto main_c, int tb) {
+        constexpr bool MAIN = decltype(main_c)::value;   // all U rows < t1 (hence < L): own-tile rows, no bounds checks on loads
+        Raw xr[U], gr[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            if (MAIN || tb + j < p.L) {
+                xr[j] = __ldcs(reinterpret_cast<const Raw *>(xp + j * xs));
+                gr[j] = __ldcs(reinterpret_cast<const Raw *>(gp + j * gs));
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int t = tb + j;
+            if (MAIN || t < tend) {
+                float2 xv[NP], gv[NP], o[NP];
+                const bool live = MAIN || t < p.L;
+                if (live) { PV::unpack(xr[j], xv); PV::unpack(gr[j], gv); }
+#pragma unroll
+                for (int i = 0; i < NP; ++i) {
+#pragma unroll
+                    for (int k = 0; k < K - 1; ++k) { win[i][k] = win[i][k + 1]; dvw[i][k] = dvw[i][k + 1]; }
+                    float2 dv = make_float2(0.f, 0.f);
+                    if (live) {
+                        win[i][K - 1] = xv[i];
+                        float2 v = bias[i];
+#pragma unroll
+                        for (int k = 0; k < K; ++k) v = ffma2(w[i][k], win[i][k], v);
+                        const float2 sg = sigmoid2(v);
+                        // d silu = sg (1 + v (1 - sg)) = sg (1 + v - v sg)
+                        const float2 vs = fmul2(v, sg);
+                        dv = fmul2(fmul2(gv[i], sg), fadd2(fadd2(v, splat2(1.0f)), make_float2(-vs.x, -vs.y)));
+                        if (MAIN || t < t1) {   // parameter gradients: own tile only
+                            db[i] = fadd2(db[i], dv);
+#pragma unroll
+                            for (int k = 0; k < K; ++k) dw[i][k] = ffma2(dv, win[i][k], dw[i][k]);
+                        }
+                    }
+                    dvw[i][K - 1] = dv;
+                    float2 acc = fmul2(w[i][0], dvw[i][K - 1]);
+#pragma unroll
+                    for (int k = 1; k < K; ++k) acc = ffma2(w[i][k], dvw[i][K - 1 - k], acc);
+                    o[i] = acc;
+                }
+                const int s_out = t - (K - 1);
+                if (s_out >= t0 && s_out < t1) __stcs(reinterpret_cast<Raw *>(dp + j * ds), PV::pack(o));
+            }
+        }
+        xp += U * xs;
+        gp += U * gs;
+        dp += U * ds;
+    };
+    int tb = t0;
+    for (; tb + U <= t1; tb += U) group(std::true_type{}, tb);
+    for (; tb < tend; tb += U) group(std::false_type{}, tb);
+    float *part = p.part + ((size_t)(b * p.ntiles + tile) * (K + 1)) * p.ED + c;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) *reinterpret_cast<float2 *>(part + (size_t)k * p.ED + 2 * i) = dw[i][k];
+        *reinterpret_cast<float2 *>(part + (size_t)K * p.ED + 2 * i) = db[i];
+    }
+}
+
 // block (32 channels, 8 slices of the B * ntiles partial rows): coalesced reads, 8-way split of the serial sum
 template <int K>
 __global__ void __launch_bounds__(256) conv1d_bwd_finalize_kernel(ConvParams p) {
@@ -241,7 +444,7 @@ static int conv_fwd_launch(ConvParams &p, cudaStream_t st) {
     const int v = conv_vec<T>(p, false);
     const dim3 block(128), grid((p.ED / v + 127) / 128, p.ntiles, p.B);
     { ScopedKernelTimer tm(K_CONV_FWD, st);
-      if (v == V) conv1d_silu_fwd_kernel<T, K, V><<<grid, block, 0, st>>>(p);
+      if (v == V) conv1d_silu_fwd_pk_kernel<T, K, V / 2><<<grid, block, 0, st>>>(p);
       else conv1d_silu_fwd_kernel<T, K, 1><<<grid, block, 0, st>>>(p); }
     return check_launch("conv1d_silu_fwd");
 }
@@ -252,7 +455,7 @@ static int conv_bwd_launch(ConvParams &p, cudaStream_t st) {
     const int v = conv_vec<T>(p, true);
     const dim3 block(128), grid((p.ED / v + 127) / 128, p.ntiles, p.B);
     { ScopedKernelTimer tm(K_CONV_BWD, st);
-      if (v == V) conv1d_silu_bwd_kernel<T, K, V><<<grid, block, 0, st>>>(p);
+      if (v == V) conv1d_silu_bwd_pk_kernel<T, K, V / 2><<<grid, block, 0, st>>>(p);
       else conv1d_silu_bwd_kernel<T, K, 1><<<grid, block, 0, st>>>(p); }
     int rc = check_launch("conv1d_silu_bwd");
     if (rc != GFE_OK) return rc;

@@ -317,6 +317,29 @@ def test_conv1d_silu(B, L, ED, K):
     assert relerr(wt.grad, dw) < 1e-4 and relerr(bt.grad, db) < 1e-4
 
 
+@pytest.mark.parametrize("dtype,K", [(torch.bfloat16, 4), (torch.float16, 3)])
+def test_conv1d_silu_half_precision(dtype, K):
+    """16-bit activations (four channels per lane, packed FP32 math): oracle on the rounded inputs, ragged L and a second tile."""
+    from gfe_mamba_b200 import causal_conv1d_silu
+    B, L, ED = 2, 203, 128
+    r = np.random.default_rng(9)
+    rnd = lambda a: torch.from_numpy(a).to(dtype).float().numpy()
+    xz = rnd(r.standard_normal((B, L, 2 * ED)).astype(np.float32))
+    w = (r.standard_normal((ED, 1, K)) * 0.5).astype(np.float32)
+    b = (r.standard_normal(ED) * 0.1).astype(np.float32)
+    du = rnd(r.standard_normal((B, L, ED)).astype(np.float32))
+    xzt = torch.from_numpy(xz).to(dtype).cuda().requires_grad_()
+    wt, bt = cuda(w, grad=True), cuda(b, grad=True)
+    u = causal_conv1d_silu(xzt[..., :ED], wt, bt)
+    u.backward(torch.from_numpy(du).to(dtype).cuda())
+    xin = np.ascontiguousarray(xz[..., :ED])
+    tol = TOL[dtype]
+    assert relerr(u, orc.conv1d_silu_fwd(xin, w, b)) < tol
+    dxin, dw, db = orc.conv1d_silu_bwd(xin, w, b, du)
+    assert relerr(xzt.grad[..., :ED], dxin) < tol
+    assert relerr(wt.grad, dw) < 1e-3 and relerr(bt.grad, db) < 1e-3   # fp32 accumulation of exactly representable inputs
+
+
 def test_conv1d_matches_torch_conv1d():
     """Same op as the reference module: nn.Conv1d(groups=ED, padding=K-1)(x^T)[:, :, :L]^T then silu (mamba.py:208-212)."""
     from gfe_mamba_b200 import causal_conv1d_silu
