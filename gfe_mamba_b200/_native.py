@@ -69,6 +69,8 @@ SIGNATURES = {
     "gfe_add_rmsnorm_fwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_float, ctypes.c_int, c_vp]),
     "gfe_add_rmsnorm_bwd_workspace_bytes": (c_sz, [c_i64, ctypes.c_int]),
     "gfe_add_rmsnorm_bwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_int, c_vp, c_sz, c_vp]),
+    "gfe_add_rmsnorm_fwd_mixed": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_int, c_vp]),
+    "gfe_add_rmsnorm_bwd_mixed": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_sz, c_vp]),
     "gfe_add_mean_pool_workspace_bytes": (c_sz, [ctypes.c_int] * 3),
     "gfe_add_mean_pool_fwd": (ctypes.c_int, [c_vp, c_vp, c_vp] + [ctypes.c_int] * 4 + [c_vp, c_sz, c_vp]),
     "gfe_mean_pool_bwd": (ctypes.c_int, [c_vp, c_vp] + [ctypes.c_int] * 4 + [c_vp]),

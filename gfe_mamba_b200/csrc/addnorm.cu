@@ -18,20 +18,26 @@ constexpr int kNormMaxVec = 8;         // 16-byte vectors per lane held in regis
 
 template <typename T> struct Vec16 { static constexpr int n = 16 / (int)sizeof(T); };
 
-template <typename T>
-__device__ __forceinline__ void load16(const T *p, float (&v)[Vec16<T>::n]) {
-    const uint4 raw = *reinterpret_cast<const uint4 *>(p);
+// N consecutive elements as ONE access of N * sizeof(T) bytes (16, or 8 when a 16-bit branch tensor rides along an fp32 stream)
+template <int BYTES> struct RawN;
+template <> struct RawN<16> { using type = uint4; };
+template <> struct RawN<8> { using type = uint2; };
+template <typename T, int N>
+__device__ __forceinline__ void loadN(const T *p, float (&v)[N]) {
+    using R = typename RawN<N * (int)sizeof(T)>::type;
+    const R raw = *reinterpret_cast<const R *>(p);
     const T *e = reinterpret_cast<const T *>(&raw);
 #pragma unroll
-    for (int i = 0; i < Vec16<T>::n; ++i) v[i] = to_f(e[i]);
+    for (int i = 0; i < N; ++i) v[i] = to_f(e[i]);
 }
-template <typename T>
-__device__ __forceinline__ void store16(T *p, const float (&v)[Vec16<T>::n]) {
-    uint4 raw;
+template <typename T, int N>
+__device__ __forceinline__ void storeN(T *p, const float (&v)[N]) {
+    using R = typename RawN<N * (int)sizeof(T)>::type;
+    R raw;
     T *e = reinterpret_cast<T *>(&raw);
 #pragma unroll
-    for (int i = 0; i < Vec16<T>::n; ++i) e[i] = from_f<T>(v[i]);
-    *reinterpret_cast<uint4 *>(p) = raw;
+    for (int i = 0; i < N; ++i) e[i] = from_f<T>(v[i]);
+    *reinterpret_cast<R *>(p) = raw;
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -39,13 +45,16 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// NV = vectors per lane (compile-time), D == any multiple of the vector width with D <= 32 * NV * VEC
-template <typename T, int NV, bool HAS_A>
-__global__ void __launch_bounds__(32 * kNormWarps) add_rmsnorm_fwd_kernel(const T *__restrict__ x, const T *__restrict__ a,
-                                                                          const float *__restrict__ w, T *__restrict__ resid,
-                                                                          T *__restrict__ y, float *__restrict__ rstd_out,
+// NV = vectors per lane (compile-time), D == any multiple of the vector width with D <= 32 * NV * VEC.
+// TR = element type of the residual stream (x, resid; backward: dres, dx), TB = element type of the branch side (a, y;
+// backward: dy, da).  TB == TR is the plain case; TR = float with a 16-bit TB is the stack under autocast: the fp32 stream
+// takes the mixer's 16-bit output and hands the next mixer a 16-bit normed input with no cast kernels in between.
+template <typename TR, typename TB, int NV, bool HAS_A>
+__global__ void __launch_bounds__(32 * kNormWarps) add_rmsnorm_fwd_kernel(const TR *__restrict__ x, const TB *__restrict__ a,
+                                                                          const float *__restrict__ w, TR *__restrict__ resid,
+                                                                          TB *__restrict__ y, float *__restrict__ rstd_out,
                                                                           int64_t rows, int D, float eps) {
-    constexpr int VEC = Vec16<T>::n;
+    constexpr int VEC = Vec16<TR>::n;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nvec = D / VEC;
     float wv[NV][VEC];
@@ -62,13 +71,13 @@ __global__ void __launch_bounds__(32 * kNormWarps) add_rmsnorm_fwd_kernel(const 
         for (int i = 0; i < NV; ++i) {
             const int v = lane + 32 * i;
             if (v < nvec) {
-                load16<T>(x + r * D + v * VEC, xv[i]);
+                loadN<TR, VEC>(x + r * D + v * VEC, xv[i]);
                 if (HAS_A) {
                     float av[VEC];
-                    load16<T>(a + r * D + v * VEC, av);
+                    loadN<TB, VEC>(a + r * D + v * VEC, av);
 #pragma unroll
-                    for (int e = 0; e < VEC; ++e) xv[i][e] = to_f(from_f<T>(xv[i][e] + av[e]));   // the stream is stored in T
-                    store16<T>(resid + r * D + v * VEC, xv[i]);
+                    for (int e = 0; e < VEC; ++e) xv[i][e] = to_f(from_f<TR>(xv[i][e] + av[e]));   // the stream is stored in TR
+                    storeN<TR, VEC>(resid + r * D + v * VEC, xv[i]);
                 }
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) ss = fmaf(xv[i][e], xv[i][e], ss);
@@ -84,18 +93,20 @@ __global__ void __launch_bounds__(32 * kNormWarps) add_rmsnorm_fwd_kernel(const 
                 float o[VEC];
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) o[e] = (xv[i][e] * rstd) * wv[i][e];   // the reference's order: (x * rstd) * w
-                store16<T>(y + r * D + v * VEC, o);
+                storeN<TB, VEC>(y + r * D + v * VEC, o);
             }
         }
     }
 }
 
-template <typename T, int NV, bool HAS_DRES>
-__global__ void __launch_bounds__(32 * kNormWarps) add_rmsnorm_bwd_kernel(const T *__restrict__ resid, const float *__restrict__ w,
-                                                                          const float *__restrict__ rstd_in, const T *__restrict__ dy,
-                                                                          const T *__restrict__ dres, T *__restrict__ dx,
-                                                                          float *__restrict__ dw_part, int64_t rows, int D) {
-    constexpr int VEC = Vec16<T>::n;
+// da (optional): the gradient of the branch operand `a` in ITS element type -- the same values as dx, rounded -- so that a
+// 16-bit branch gets its gradient from this pass instead of a cast kernel over dx.
+template <typename TR, typename TB, int NV, bool HAS_DRES>
+__global__ void __launch_bounds__(32 * kNormWarps) add_rmsnorm_bwd_kernel(const TR *__restrict__ resid, const float *__restrict__ w,
+                                                                          const float *__restrict__ rstd_in, const TB *__restrict__ dy,
+                                                                          const TR *__restrict__ dres, TR *__restrict__ dx,
+                                                                          TB *__restrict__ da, float *__restrict__ dw_part, int64_t rows, int D) {
+    constexpr int VEC = Vec16<TR>::n;
     __shared__ float s_dw[kNormWarps][32 * VEC + 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nvec = D / VEC;
@@ -120,8 +131,8 @@ __global__ void __launch_bounds__(32 * kNormWarps) add_rmsnorm_bwd_kernel(const 
         for (int i = 0; i < NV; ++i) {
             const int v = lane + 32 * i;
             if (v < nvec) {
-                load16<T>(resid + r * D + v * VEC, xv[i]);
-                load16<T>(dy + r * D + v * VEC, gv[i]);
+                loadN<TR, VEC>(resid + r * D + v * VEC, xv[i]);
+                loadN<TB, VEC>(dy + r * D + v * VEC, gv[i]);
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) {
                     dwv[i][e] = fmaf(gv[i][e], xv[i][e] * rstd, dwv[i][e]);
@@ -140,11 +151,12 @@ __global__ void __launch_bounds__(32 * kNormWarps) add_rmsnorm_bwd_kernel(const 
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) o[e] = rstd * (gv[i][e] - xv[i][e] * c);
                 if (HAS_DRES) {
-                    const T *dv = reinterpret_cast<const T *>(&dv_raw[i]);
+                    const TR *dv = reinterpret_cast<const TR *>(&dv_raw[i]);
 #pragma unroll
                     for (int e = 0; e < VEC; ++e) o[e] += to_f(dv[e]);
                 }
-                store16<T>(dx + r * D + v * VEC, o);
+                storeN<TR, VEC>(dx + r * D + v * VEC, o);
+                if (da != nullptr) storeN<TB, VEC>(da + r * D + v * VEC, o);
             }
         }
     }
@@ -200,19 +212,19 @@ static int nv_for(int D) {
     return 0;
 }
 
-template <typename T>
+template <typename TR, typename TB>
 static int launch_fwd_t(const void *x, const void *a, const float *w, void *resid, void *y, float *rstd, int64_t rows, int D,
                         float eps, cudaStream_t st) {
-    const int nv = nv_for<T>(D);
+    const int nv = nv_for<TR>(D);
     if (nv == 0) {
-        set_error("add_rmsnorm: d_model=%d must be a multiple of %d and at most %d for this dtype", D, Vec16<T>::n, 256 * Vec16<T>::n);
+        set_error("add_rmsnorm: d_model=%d must be a multiple of %d and at most %d for this dtype", D, Vec16<TR>::n, 256 * Vec16<TR>::n);
         return GFE_ERR_ARG;
     }
     const int grid = norm_grid(rows);
     ScopedKernelTimer tm(K_ADDNORM_FWD, st);
 #define GFE_NF(NVv)                                                                                                          \
-    if (a) add_rmsnorm_fwd_kernel<T, NVv, true><<<grid, 32 * kNormWarps, 0, st>>>((const T *)x, (const T *)a, w, (T *)resid, (T *)y, rstd, rows, D, eps); \
-    else add_rmsnorm_fwd_kernel<T, NVv, false><<<grid, 32 * kNormWarps, 0, st>>>((const T *)x, nullptr, w, nullptr, (T *)y, rstd, rows, D, eps)
+    if (a) add_rmsnorm_fwd_kernel<TR, TB, NVv, true><<<grid, 32 * kNormWarps, 0, st>>>((const TR *)x, (const TB *)a, w, (TR *)resid, (TB *)y, rstd, rows, D, eps); \
+    else add_rmsnorm_fwd_kernel<TR, TB, NVv, false><<<grid, 32 * kNormWarps, 0, st>>>((const TR *)x, nullptr, w, nullptr, (TB *)y, rstd, rows, D, eps)
     switch (nv) {
         case 1: GFE_NF(1); break;
         case 2: GFE_NF(2); break;
@@ -225,12 +237,12 @@ static int launch_fwd_t(const void *x, const void *a, const float *w, void *resi
     return check_launch("add_rmsnorm_fwd");
 }
 
-template <typename T>
-static int launch_bwd_t(const void *resid, const float *w, const float *rstd, const void *dy, const void *dres, void *dx, float *dw,
-                        int64_t rows, int D, void *ws, size_t ws_bytes, cudaStream_t st) {
-    const int nv = nv_for<T>(D);
+template <typename TR, typename TB>
+static int launch_bwd_t(const void *resid, const float *w, const float *rstd, const void *dy, const void *dres, void *dx, void *da,
+                        float *dw, int64_t rows, int D, void *ws, size_t ws_bytes, cudaStream_t st) {
+    const int nv = nv_for<TR>(D);
     if (nv == 0) {
-        set_error("add_rmsnorm: d_model=%d must be a multiple of %d and at most %d for this dtype", D, Vec16<T>::n, 256 * Vec16<T>::n);
+        set_error("add_rmsnorm: d_model=%d must be a multiple of %d and at most %d for this dtype", D, Vec16<TR>::n, 256 * Vec16<TR>::n);
         return GFE_ERR_ARG;
     }
     const int grid = norm_grid(rows);
@@ -243,8 +255,8 @@ static int launch_bwd_t(const void *resid, const float *w, const float *rstd, co
     {
         ScopedKernelTimer tm(K_ADDNORM_BWD, st);
 #define GFE_NB(NVv)                                                                                                          \
-    if (dres) add_rmsnorm_bwd_kernel<T, NVv, true><<<grid, 32 * kNormWarps, 0, st>>>((const T *)resid, w, rstd, (const T *)dy, (const T *)dres, (T *)dx, part, rows, D); \
-    else add_rmsnorm_bwd_kernel<T, NVv, false><<<grid, 32 * kNormWarps, 0, st>>>((const T *)resid, w, rstd, (const T *)dy, nullptr, (T *)dx, part, rows, D)
+    if (dres) add_rmsnorm_bwd_kernel<TR, TB, NVv, true><<<grid, 32 * kNormWarps, 0, st>>>((const TR *)resid, w, rstd, (const TB *)dy, (const TR *)dres, (TR *)dx, (TB *)da, part, rows, D); \
+    else add_rmsnorm_bwd_kernel<TR, TB, NVv, false><<<grid, 32 * kNormWarps, 0, st>>>((const TR *)resid, w, rstd, (const TB *)dy, nullptr, (TR *)dx, (TB *)da, part, rows, D)
         switch (nv) {
             case 1: GFE_NB(1); break;
             case 2: GFE_NB(2); break;
@@ -276,8 +288,8 @@ GFE_API size_t gfe_add_rmsnorm_bwd_workspace_bytes(int64_t rows, int D) {
     return (size_t)norm_grid(rows) * (size_t)(D > 0 ? D : 0) * sizeof(float);
 }
 
-GFE_API int gfe_add_rmsnorm_fwd(const void *x, const void *a, const float *w, void *resid, void *y, float *rstd, int64_t rows,
-                                int D, float eps, int dtype, void *stream) {
+GFE_API int gfe_add_rmsnorm_fwd_mixed(const void *x, const void *a, const float *w, void *resid, void *y, float *rstd, int64_t rows,
+                                      int D, float eps, int res_dtype, int io_dtype, void *stream) {
     if (x == nullptr || w == nullptr || y == nullptr || rows < 0 || D <= 0 || (a != nullptr && resid == nullptr)) {
         set_error("add_rmsnorm_fwd: bad argument");
         return GFE_ERR_ARG;
@@ -288,31 +300,56 @@ GFE_API int gfe_add_rmsnorm_fwd(const void *x, const void *a, const float *w, vo
     }
     if (rows == 0) return GFE_OK;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    switch (dtype) {
-        case GFE_F32: return launch_fwd_t<float>(x, a, w, resid, y, rstd, rows, D, eps, st);
-        case GFE_BF16: return launch_fwd_t<__nv_bfloat16>(x, a, w, resid, y, rstd, rows, D, eps, st);
-        case GFE_F16: return launch_fwd_t<__half>(x, a, w, resid, y, rstd, rows, D, eps, st);
-        default: set_error("add_rmsnorm_fwd: unsupported dtype %d", dtype); return GFE_ERR_DTYPE;
+    if (res_dtype == io_dtype) {
+        switch (res_dtype) {
+            case GFE_F32: return launch_fwd_t<float, float>(x, a, w, resid, y, rstd, rows, D, eps, st);
+            case GFE_BF16: return launch_fwd_t<__nv_bfloat16, __nv_bfloat16>(x, a, w, resid, y, rstd, rows, D, eps, st);
+            case GFE_F16: return launch_fwd_t<__half, __half>(x, a, w, resid, y, rstd, rows, D, eps, st);
+            default: break;
+        }
+    } else if (res_dtype == GFE_F32) {
+        if (io_dtype == GFE_BF16) return launch_fwd_t<float, __nv_bfloat16>(x, a, w, resid, y, rstd, rows, D, eps, st);
+        if (io_dtype == GFE_F16) return launch_fwd_t<float, __half>(x, a, w, resid, y, rstd, rows, D, eps, st);
     }
+    set_error("add_rmsnorm_fwd: unsupported dtype pair (stream %d, branch %d)", res_dtype, io_dtype);
+    return GFE_ERR_DTYPE;
 }
 
-GFE_API int gfe_add_rmsnorm_bwd(const void *resid, const float *w, const float *rstd, const void *dy, const void *dres, void *dx,
-                                float *dw, int64_t rows, int D, int dtype, void *ws, size_t ws_bytes, void *stream) {
+GFE_API int gfe_add_rmsnorm_fwd(const void *x, const void *a, const float *w, void *resid, void *y, float *rstd, int64_t rows,
+                                int D, float eps, int dtype, void *stream) {
+    return gfe_add_rmsnorm_fwd_mixed(x, a, w, resid, y, rstd, rows, D, eps, dtype, dtype, stream);
+}
+
+GFE_API int gfe_add_rmsnorm_bwd_mixed(const void *resid, const float *w, const float *rstd, const void *dy, const void *dres, void *dx,
+                                      void *da, float *dw, int64_t rows, int D, int res_dtype, int io_dtype, void *ws,
+                                      size_t ws_bytes, void *stream) {
     if (resid == nullptr || w == nullptr || rstd == nullptr || dy == nullptr || dx == nullptr || dw == nullptr || rows <= 0 || D <= 0) {
         set_error("add_rmsnorm_bwd: bad argument");
         return GFE_ERR_ARG;
     }
-    if (!aligned16(resid) || !aligned16(dy) || !aligned16(dres) || !aligned16(dx)) {
+    if (!aligned16(resid) || !aligned16(dy) || !aligned16(dres) || !aligned16(dx) || !aligned16(da)) {
         set_error("add_rmsnorm_bwd: tensors must be 16-byte aligned and row-contiguous");
         return GFE_ERR_ARG;
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    switch (dtype) {
-        case GFE_F32: return launch_bwd_t<float>(resid, w, rstd, dy, dres, dx, dw, rows, D, ws, ws_bytes, st);
-        case GFE_BF16: return launch_bwd_t<__nv_bfloat16>(resid, w, rstd, dy, dres, dx, dw, rows, D, ws, ws_bytes, st);
-        case GFE_F16: return launch_bwd_t<__half>(resid, w, rstd, dy, dres, dx, dw, rows, D, ws, ws_bytes, st);
-        default: set_error("add_rmsnorm_bwd: unsupported dtype %d", dtype); return GFE_ERR_DTYPE;
+    if (res_dtype == io_dtype) {
+        switch (res_dtype) {
+            case GFE_F32: return launch_bwd_t<float, float>(resid, w, rstd, dy, dres, dx, da, dw, rows, D, ws, ws_bytes, st);
+            case GFE_BF16: return launch_bwd_t<__nv_bfloat16, __nv_bfloat16>(resid, w, rstd, dy, dres, dx, da, dw, rows, D, ws, ws_bytes, st);
+            case GFE_F16: return launch_bwd_t<__half, __half>(resid, w, rstd, dy, dres, dx, da, dw, rows, D, ws, ws_bytes, st);
+            default: break;
+        }
+    } else if (res_dtype == GFE_F32) {
+        if (io_dtype == GFE_BF16) return launch_bwd_t<float, __nv_bfloat16>(resid, w, rstd, dy, dres, dx, da, dw, rows, D, ws, ws_bytes, st);
+        if (io_dtype == GFE_F16) return launch_bwd_t<float, __half>(resid, w, rstd, dy, dres, dx, da, dw, rows, D, ws, ws_bytes, st);
     }
+    set_error("add_rmsnorm_bwd: unsupported dtype pair (stream %d, branch %d)", res_dtype, io_dtype);
+    return GFE_ERR_DTYPE;
+}
+
+GFE_API int gfe_add_rmsnorm_bwd(const void *resid, const float *w, const float *rstd, const void *dy, const void *dres, void *dx,
+                                float *dw, int64_t rows, int D, int dtype, void *ws, size_t ws_bytes, void *stream) {
+    return gfe_add_rmsnorm_bwd_mixed(resid, w, rstd, dy, dres, dx, nullptr, dw, rows, D, dtype, dtype, ws, ws_bytes, stream);
 }
 
 }  // extern "C"

@@ -421,31 +421,39 @@ def mamba_inner_fn(xz: torch.Tensor, conv_w: torch.Tensor, conv_b: Optional[torc
 # ----------------------------------------------------------------- residual add + RMSNorm
 class _AddRMSNormFn(torch.autograd.Function):
     """resid = x (+ a);  y = (resid * rsqrt(mean(resid^2) + eps)) * w -- the residual add of ResidualBlock.forward
-    (cross_atten/mamba.py:103) fused with the next RMSNorm (mamba.py:408-418).  SURVEY 8f rank 1."""
+    (cross_atten/mamba.py:103) fused with the next RMSNorm (mamba.py:408-418).  SURVEY 8f rank 1.
+
+    Two element types: the residual stream (x, resid and their gradients) keeps x's dtype; the branch side (a, y and their
+    gradients) may be 16-bit next to an fp32 stream -- the stack under autocast -- so that neither the mixer's 16-bit output
+    nor the normed input of the next mixer passes through a cast kernel."""
 
     @staticmethod
-    def forward(ctx, x, a, weight, eps: float, grad_mode: bool):
+    def forward(ctx, x, a, weight, eps: float, grad_mode: bool, io_dtype):
         dev = _require_cuda(x, a, weight)
         if x.dtype not in _DT:
             raise TypeError(f"add_rmsnorm: unsupported activation dtype {x.dtype}")
         D = x.shape[-1]
         if weight.shape != (D,) or (a is not None and a.shape != x.shape):
             raise ValueError("add_rmsnorm: inconsistent shapes")
+        if io_dtype != x.dtype and not (x.dtype == torch.float32 and io_dtype in (torch.bfloat16, torch.float16)):
+            raise TypeError(f"add_rmsnorm: stream {x.dtype} with branch {io_dtype} is not supported")
         x_ = x.detach().contiguous()
-        a_ = None if a is None else a.detach().to(x.dtype).contiguous()
+        a_ = None if a is None else a.detach().to(io_dtype).contiguous()
         w_ = _f32(weight)
         rows = x_.numel() // D
         resid = torch.empty_like(x_) if a_ is not None else x_
-        y = torch.empty_like(x_)
+        y = torch.empty(x_.shape, dtype=io_dtype, device=dev)
         need_grad = grad_mode and any(ctx.needs_input_grad)
         rstd = torch.empty(rows, dtype=torch.float32, device=dev) if need_grad else None
         l = nat.lib()
         with torch.cuda.device(dev):
-            nat.check(l.gfe_add_rmsnorm_fwd(_ptr(x_), _ptr(a_), _ptr(w_), _ptr(resid if a_ is not None else None), _ptr(y),
-                                            _ptr(rstd), rows, D, float(eps), _DT[x.dtype], _stream(dev)), "add_rmsnorm_fwd")
+            nat.check(l.gfe_add_rmsnorm_fwd_mixed(_ptr(x_), _ptr(a_), _ptr(w_), _ptr(resid if a_ is not None else None), _ptr(y),
+                                                  _ptr(rstd), rows, D, float(eps), _DT[x.dtype], _DT[io_dtype], _stream(dev)),
+                      "add_rmsnorm_fwd")
         if need_grad:
             ctx.save_for_backward(resid, w_, rstd)
-            ctx.has_a = a is not None
+            ctx.a_dtype = None if a is None else a.dtype
+            ctx.io_dtype = io_dtype
             ctx.wdtype = weight.dtype
         return resid, y
 
@@ -455,23 +463,44 @@ class _AddRMSNormFn(torch.autograd.Function):
         dev = resid.device
         D = resid.shape[-1]
         rows = resid.numel() // D
-        dy_ = torch.zeros_like(resid) if dy is None else dy.detach().to(resid.dtype).contiguous()
+        io = ctx.io_dtype
+        dy_ = torch.zeros(resid.shape, dtype=io, device=dev) if dy is None else dy.detach().to(io).contiguous()
         dres_ = None if dresid is None else dresid.detach().to(resid.dtype).contiguous()
         dx = torch.empty_like(resid)
+        # the branch operand's gradient in ITS dtype comes out of the same pass when that dtype differs from the stream's
+        da = torch.empty(resid.shape, dtype=io, device=dev) if (ctx.a_dtype is not None and io != resid.dtype) else None
         dw = torch.empty(D, dtype=torch.float32, device=dev)
         l = nat.lib()
         with torch.cuda.device(dev):
             nws = l.gfe_add_rmsnorm_bwd_workspace_bytes(rows, D)
             ws = _bytes(nws, dev)
-            nat.check(l.gfe_add_rmsnorm_bwd(_ptr(resid), _ptr(w_), _ptr(rstd), _ptr(dy_), _ptr(dres_), _ptr(dx), _ptr(dw), rows, D,
-                                            _DT[resid.dtype], _ptr(ws), nws, _stream(dev)), "add_rmsnorm_bwd")
-        return dx, (dx if ctx.has_a else None), dw.to(ctx.wdtype), None, None
+            nat.check(l.gfe_add_rmsnorm_bwd_mixed(_ptr(resid), _ptr(w_), _ptr(rstd), _ptr(dy_), _ptr(dres_), _ptr(dx), _ptr(da),
+                                                  _ptr(dw), rows, D, _DT[resid.dtype], _DT[io], _ptr(ws), nws, _stream(dev)),
+                      "add_rmsnorm_bwd")
+        if ctx.a_dtype is None:
+            ga = None
+        elif da is not None:
+            ga = da if ctx.a_dtype == io else da.to(ctx.a_dtype)
+        else:
+            ga = dx if ctx.a_dtype == dx.dtype else dx.to(ctx.a_dtype)
+        return dx, ga, dw.to(ctx.wdtype), None, None, None
 
 
-def add_rmsnorm(x: torch.Tensor, a: Optional[torch.Tensor], weight: torch.Tensor, eps: float = 1e-5
-                ) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Returns (resid, y): resid = x + a (or x itself when a is None), y = RMSNorm(resid) * weight.  x, a: (..., D)."""
-    return _AddRMSNormFn.apply(x, a, weight, eps, torch.is_grad_enabled())
+def add_rmsnorm(x: torch.Tensor, a: Optional[torch.Tensor], weight: torch.Tensor, eps: float = 1e-5,
+                out_dtype: Optional[torch.dtype] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Returns (resid, y): resid = x + a (or x itself when a is None) in x's dtype, y = RMSNorm(resid) * weight.  x, a: (..., D).
+
+    ``out_dtype`` is the dtype of ``y`` (and the dtype ``a`` is read in).  By default it is x's dtype, except for an fp32
+    stream under CUDA autocast whose branch ``a`` is absent or already in the autocast dtype: then ``y`` comes out in that
+    dtype -- what the next ``nn.Linear`` would cast it to anyway (same rounding of the same fp32 value) -- and ``a`` is
+    consumed as it is."""
+    if out_dtype is None:
+        out_dtype = x.dtype
+        if x.dtype == torch.float32 and x.is_cuda and torch.is_autocast_enabled("cuda"):
+            ad = torch.get_autocast_dtype("cuda")
+            if ad in (torch.bfloat16, torch.float16) and (a is None or a.dtype == ad):
+                out_dtype = ad
+    return _AddRMSNormFn.apply(x, a, weight, eps, torch.is_grad_enabled(), out_dtype)
 
 
 # --------------------------------------------------------- final residual add + mean over L

@@ -158,6 +158,16 @@ GFE_API size_t gfe_add_rmsnorm_bwd_workspace_bytes(int64_t rows, int D);
 GFE_API int gfe_add_rmsnorm_bwd(const void *resid, const float *w, const float *rstd, const void *dy, const void *dres,
                                 void *dx, float *dw, int64_t rows, int D, int dtype, void *ws, size_t ws_bytes,
                                 void *stream);
+/* The same with two element types: the residual stream (x, resid, dres, dx: res_dtype) and the branch side (a, y, dy, da:
+ * io_dtype).  res_dtype == io_dtype is the call above; res_dtype = GFE_F32 with a 16-bit io_dtype is the Mamba stack under
+ * autocast (fp32 residual stream, mixers in bf16 / fp16, mamba.py:103 + :408-418 as autocast runs them): the cast kernels
+ * around the norm disappear.  D: multiple of 16 / sizeof(res element).  da (optional): the gradient of `a` in io_dtype
+ * (the values of dx, rounded). */
+GFE_API int gfe_add_rmsnorm_fwd_mixed(const void *x, const void *a, const float *w, void *resid, void *y, float *rstd,
+                                      int64_t rows, int D, float eps, int res_dtype, int io_dtype, void *stream);
+GFE_API int gfe_add_rmsnorm_bwd_mixed(const void *resid, const float *w, const float *rstd, const void *dy, const void *dres,
+                                      void *dx, void *da, float *dw, int64_t rows, int D, int res_dtype, int io_dtype,
+                                      void *ws, size_t ws_bytes, void *stream);
 
 /* ------------------------------------ final residual add + mean over L (head) --
  * out[b, d] = mean_t (a[b, t, d] + r[b, t, d]): the last residual add of the Mamba stack (mamba.py:103) fused with the

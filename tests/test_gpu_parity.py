@@ -575,6 +575,46 @@ def test_add_rmsnorm_vs_torch(rows, D, dtype, with_add):
         assert relerr(a.grad, ad.grad) < tol
 
 
+@pytest.mark.parametrize("rows,D,io", [(300, 512, torch.bfloat16), (37, 768, torch.float16), (5, 4, torch.bfloat16)])
+@pytest.mark.parametrize("with_add", [True, False])
+def test_add_rmsnorm_mixed_dtypes(rows, D, io, with_add):
+    """fp32 residual stream with a 16-bit branch (the stack under autocast): resid = x + a in fp32, y in the branch dtype;
+    backward dx in fp32 and da in the branch dtype from the same pass.  Against torch fp64 on the inputs as the kernel sees them."""
+    from gfe_mamba_b200 import add_rmsnorm
+    g = torch.Generator(device="cpu").manual_seed(rows + D)
+    x = torch.randn(rows, D, generator=g).cuda().requires_grad_()
+    a = torch.randn(rows, D, generator=g).to(io).cuda().requires_grad_() if with_add else None
+    w = (1 + 0.1 * torch.randn(D, generator=g)).cuda().requires_grad_()
+    dres, dy = torch.randn(rows, D, generator=g).cuda(), torch.randn(rows, D, generator=g).to(io).cuda()
+    resid, y = add_rmsnorm(x, a, w, 1e-5, out_dtype=io)
+    assert resid.dtype == torch.float32 and y.dtype == io
+    (resid * dres).sum().add((y.float() * dy.float()).sum()).backward()
+    xd = x.detach().double().requires_grad_()
+    ad = a.detach().double().requires_grad_() if with_add else None
+    wd = w.detach().double().requires_grad_()
+    rd = (xd + ad).detach().float().double() + ((xd + ad) - (xd + ad).detach()) if with_add else xd
+    yd = rd * torch.rsqrt(rd.pow(2).mean(-1, keepdim=True) + 1e-5) * wd
+    ((rd * dres.double()).sum() + (yd * dy.double()).sum()).backward()
+    assert relerr(resid, rd.detach()) < 1e-6 and relerr(y, yd.detach()) < TOL[io]
+    assert relerr(x.grad, xd.grad) < 1e-5 and relerr(w.grad, wd.grad) < 1e-4
+    if with_add:
+        assert a.grad.dtype == io and relerr(a.grad, ad.grad) < TOL[io]
+        assert torch.equal(a.grad, x.grad.to(io))            # the same values, rounded once
+
+
+def test_add_rmsnorm_picks_the_autocast_dtype():
+    """Under CUDA autocast an fp32 stream hands the next mixer its input in the autocast dtype (no cast kernel), and only then."""
+    from gfe_mamba_b200 import add_rmsnorm
+    x = torch.randn(8, 64, device="cuda")
+    w = torch.ones(64, device="cuda")
+    assert add_rmsnorm(x, None, w)[1].dtype == torch.float32
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        assert add_rmsnorm(x, None, w)[1].dtype == torch.bfloat16
+        assert add_rmsnorm(x, x.bfloat16(), w)[1].dtype == torch.bfloat16
+        assert add_rmsnorm(x, x, w)[1].dtype == torch.float32          # an fp32 branch is not rounded behind the caller's back
+        assert add_rmsnorm(x.bfloat16(), None, w)[1].dtype == torch.bfloat16
+
+
 def test_mamba_stack_fused_norm_matches_layerwise():
     """Mamba.forward with the residual adds fused into the next RMSNorm == the reference's layer-by-layer formulation."""
     from gfe_mamba_b200 import Mamba, MambaConfig
