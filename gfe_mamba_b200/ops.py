@@ -328,7 +328,8 @@ class _MambaInnerFn(torch.autograd.Function):
         l = nat.lib()
         u = torch.empty((B, L, ED), dtype=dt, device=dev)
         out = torch.empty((B, L, ED), dtype=dt, device=dev)
-        with torch.cuda.device(dev):
+        # the GEMMs run in the activation dtype chosen above whatever the ambient autocast state (the kernels need one dtype)
+        with torch.cuda.device(dev), torch.autocast("cuda", enabled=False):
             nat.check(l.gfe_conv1d_silu_fwd(_ptr(xin), xin.stride(0), xin.stride(1), _ptr(cw), _ptr(cb), _ptr(u), u.stride(0),
                                             u.stride(1), B, L, ED, K, _DT[dt], _stream(dev)), "conv1d_silu_fwd")
             dbc = torch.mm(u.view(B * L, ED), Wx.t())                 # (B L, R + 2N): delta_low | B | C
@@ -377,7 +378,7 @@ class _MambaInnerFn(torch.autograd.Function):
         dcb = None if cb is None else torch.empty((ED,), dtype=torch.float32, device=dev)
         dbc3 = dbc.view(B, L, R + 2 * N)
         l = nat.lib()
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), torch.autocast("cuda", enabled=False):
             a = nat.SelscanArgs()
             _fill_common(a, u, delta, z, dbc3[..., R:R + N], dbc3[..., R + N:], A_log_, D_, bias_, True)
             a.ckpt, a.ckpt_bytes = ckpt.data_ptr(), ckpt.numel()
