@@ -179,6 +179,106 @@ __global__ void __launch_bounds__(32 * kNormWarps) add_rmsnorm_bwd_kernel(const 
     }
 }
 
+// ---- rows wider than the register-resident form (D > 256 vectors): two passes over the row, the second one from L1/L2 ----
+// Same arithmetic and element types; one warp per row.  dw comes from a separate column pass (dw_wide) because per-lane
+// accumulators for a whole row no longer fit in registers.
+template <typename TR, typename TB, bool HAS_A>
+__global__ void __launch_bounds__(32 * kNormWarps) add_rmsnorm_fwd_wide_kernel(const TR *__restrict__ x, const TB *__restrict__ a,
+                                                                               const float *__restrict__ w, TR *__restrict__ resid,
+                                                                               TB *__restrict__ y, float *__restrict__ rstd_out,
+                                                                               int64_t rows, int D, float eps) {
+    constexpr int VEC = Vec16<TR>::n;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nvec = D / VEC;
+    for (int64_t r = (int64_t)blockIdx.x * kNormWarps + warp; r < rows; r += (int64_t)gridDim.x * kNormWarps) {
+        float ss = 0.f;
+        for (int v = lane; v < nvec; v += 32) {
+            float xv[VEC];
+            loadN<TR, VEC>(x + r * D + v * VEC, xv);
+            if (HAS_A) {
+                float av[VEC];
+                loadN<TB, VEC>(a + r * D + v * VEC, av);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) xv[e] = to_f(from_f<TR>(xv[e] + av[e]));
+                storeN<TR, VEC>(resid + r * D + v * VEC, xv);
+            }
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) ss = fmaf(xv[e], xv[e], ss);
+        }
+        ss = warp_sum(ss);
+        const float rstd = rsqrtf(ss / (float)D + eps);
+        if (lane == 0 && rstd_out != nullptr) rstd_out[r] = rstd;
+        __syncwarp();   // this warp's stores of resid are read back below by other lanes' loops only through the same addresses
+        const TR *src = HAS_A ? resid : x;
+        for (int v = lane; v < nvec; v += 32) {
+            float xv[VEC], o[VEC];
+            loadN<TR, VEC>(src + r * D + v * VEC, xv);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) o[e] = (xv[e] * rstd) * __ldg(w + v * VEC + e);
+            storeN<TB, VEC>(y + r * D + v * VEC, o);
+        }
+    }
+}
+
+template <typename TR, typename TB, bool HAS_DRES>
+__global__ void __launch_bounds__(32 * kNormWarps) add_rmsnorm_bwd_wide_kernel(const TR *__restrict__ resid, const float *__restrict__ w,
+                                                                               const float *__restrict__ rstd_in, const TB *__restrict__ dy,
+                                                                               const TR *__restrict__ dres, TR *__restrict__ dx,
+                                                                               TB *__restrict__ da, int64_t rows, int D) {
+    constexpr int VEC = Vec16<TR>::n;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nvec = D / VEC;
+    for (int64_t r = (int64_t)blockIdx.x * kNormWarps + warp; r < rows; r += (int64_t)gridDim.x * kNormWarps) {
+        const float rstd = rstd_in[r];
+        float dot = 0.f;
+        for (int v = lane; v < nvec; v += 32) {
+            float xv[VEC], gv[VEC];
+            loadN<TR, VEC>(resid + r * D + v * VEC, xv);
+            loadN<TB, VEC>(dy + r * D + v * VEC, gv);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) dot = fmaf(gv[e] * __ldg(w + v * VEC + e), xv[e], dot);
+        }
+        dot = warp_sum(dot);
+        const float c = dot / (float)D * rstd * rstd;
+        for (int v = lane; v < nvec; v += 32) {
+            float xv[VEC], gv[VEC], o[VEC];
+            loadN<TR, VEC>(resid + r * D + v * VEC, xv);
+            loadN<TB, VEC>(dy + r * D + v * VEC, gv);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) o[e] = rstd * (gv[e] * __ldg(w + v * VEC + e) - xv[e] * c);
+            if (HAS_DRES) {
+                float dv[VEC];
+                loadN<TR, VEC>(dres + r * D + v * VEC, dv);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) o[e] += dv[e];
+            }
+            storeN<TR, VEC>(dx + r * D + v * VEC, o);
+            if (da != nullptr) storeN<TB, VEC>(da + r * D + v * VEC, o);
+        }
+    }
+}
+
+// partial rows of dw[j] = sum_r dy[r, j] resid[r, j] rstd[r]: block (32 columns, 8 row lanes), gridDim.y row slices
+template <typename TR, typename TB>
+__global__ void __launch_bounds__(256) add_rmsnorm_dw_wide_kernel(const TR *__restrict__ resid, const float *__restrict__ rstd,
+                                                                  const TB *__restrict__ dy, float *__restrict__ part, int64_t rows, int D) {
+    __shared__ float s_acc[8][33];
+    const int col = blockIdx.x * 32 + threadIdx.x;
+    const int64_t per = (rows + gridDim.y - 1) / gridDim.y;
+    const int64_t r0 = (int64_t)blockIdx.y * per, r1 = r0 + per < rows ? r0 + per : rows;
+    float s = 0.f;
+    if (col < D)
+        for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) s = fmaf(to_f(dy[r * D + col]) * to_f(resid[r * D + col]), rstd[r], s);
+    s_acc[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && col < D) {
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t += s_acc[q][threadIdx.x];
+        part[(size_t)blockIdx.y * D + col] = t;
+    }
+}
+
 // block (32 columns, 8 slices of the partial rows): coalesced 128-byte reads, 8-way split of the serial sum
 __global__ void add_rmsnorm_dw_finalize_kernel(const float *__restrict__ part, float *__restrict__ dw, int nparts, int D) {
     __shared__ float s_acc[8][33];
@@ -216,12 +316,17 @@ template <typename TR, typename TB>
 static int launch_fwd_t(const void *x, const void *a, const float *w, void *resid, void *y, float *rstd, int64_t rows, int D,
                         float eps, cudaStream_t st) {
     const int nv = nv_for<TR>(D);
-    if (nv == 0) {
-        set_error("add_rmsnorm: d_model=%d must be a multiple of %d and at most %d for this dtype", D, Vec16<TR>::n, 256 * Vec16<TR>::n);
+    if (D % Vec16<TR>::n != 0) {
+        set_error("add_rmsnorm: d_model=%d must be a multiple of %d for this dtype", D, Vec16<TR>::n);
         return GFE_ERR_ARG;
     }
     const int grid = norm_grid(rows);
     ScopedKernelTimer tm(K_ADDNORM_FWD, st);
+    if (nv == 0) {   // wider than the register-resident form
+        if (a) add_rmsnorm_fwd_wide_kernel<TR, TB, true><<<grid, 32 * kNormWarps, 0, st>>>((const TR *)x, (const TB *)a, w, (TR *)resid, (TB *)y, rstd, rows, D, eps);
+        else add_rmsnorm_fwd_wide_kernel<TR, TB, false><<<grid, 32 * kNormWarps, 0, st>>>((const TR *)x, nullptr, w, nullptr, (TB *)y, rstd, rows, D, eps);
+        return check_launch("add_rmsnorm_fwd (wide)");
+    }
 #define GFE_NF(NVv)                                                                                                          \
     if (a) add_rmsnorm_fwd_kernel<TR, TB, NVv, true><<<grid, 32 * kNormWarps, 0, st>>>((const TR *)x, (const TB *)a, w, (TR *)resid, (TB *)y, rstd, rows, D, eps); \
     else add_rmsnorm_fwd_kernel<TR, TB, NVv, false><<<grid, 32 * kNormWarps, 0, st>>>((const TR *)x, nullptr, w, nullptr, (TB *)y, rstd, rows, D, eps)
@@ -241,8 +346,8 @@ template <typename TR, typename TB>
 static int launch_bwd_t(const void *resid, const float *w, const float *rstd, const void *dy, const void *dres, void *dx, void *da,
                         float *dw, int64_t rows, int D, void *ws, size_t ws_bytes, cudaStream_t st) {
     const int nv = nv_for<TR>(D);
-    if (nv == 0) {
-        set_error("add_rmsnorm: d_model=%d must be a multiple of %d and at most %d for this dtype", D, Vec16<TR>::n, 256 * Vec16<TR>::n);
+    if (D % Vec16<TR>::n != 0) {
+        set_error("add_rmsnorm: d_model=%d must be a multiple of %d for this dtype", D, Vec16<TR>::n);
         return GFE_ERR_ARG;
     }
     const int grid = norm_grid(rows);
@@ -252,6 +357,22 @@ static int launch_bwd_t(const void *resid, const float *w, const float *rstd, co
         return GFE_ERR_WORKSPACE;
     }
     float *part = reinterpret_cast<float *>(ws);
+    if (nv == 0) {   // wider than the register-resident form: dx (+ da) per row, dw from a column pass over row slices
+        const int slices = grid < 64 ? grid : 64;
+        {
+            ScopedKernelTimer tm(K_ADDNORM_BWD, st);
+            if (dres) add_rmsnorm_bwd_wide_kernel<TR, TB, true><<<grid, 32 * kNormWarps, 0, st>>>((const TR *)resid, w, rstd, (const TB *)dy, (const TR *)dres, (TR *)dx, (TB *)da, rows, D);
+            else add_rmsnorm_bwd_wide_kernel<TR, TB, false><<<grid, 32 * kNormWarps, 0, st>>>((const TR *)resid, w, rstd, (const TB *)dy, nullptr, (TR *)dx, (TB *)da, rows, D);
+            add_rmsnorm_dw_wide_kernel<TR, TB><<<dim3((D + 31) / 32, slices), dim3(32, 8), 0, st>>>((const TR *)resid, rstd, (const TB *)dy, part, rows, D);
+        }
+        int rcw = check_launch("add_rmsnorm_bwd (wide)");
+        if (rcw != GFE_OK) return rcw;
+        {
+            ScopedKernelTimer tm(K_ADDNORM_BWD_FIN, st);
+            add_rmsnorm_dw_finalize_kernel<<<(D + 31) / 32, dim3(32, 8), 0, st>>>(part, dw, slices, D);
+        }
+        return check_launch("add_rmsnorm_dw_finalize");
+    }
     {
         ScopedKernelTimer tm(K_ADDNORM_BWD, st);
 #define GFE_NB(NVv)                                                                                                          \

@@ -23,10 +23,11 @@ from .pscan import pscan
 
 
 def _fusable_norm(x: torch.Tensor, config) -> bool:
-    """The fused add + RMSNorm kernel handles 16-byte vector rows held in registers (ops.add_rmsnorm); anything else
-    takes the module-by-module path."""
+    """The fused add + RMSNorm kernels move rows as 16-byte vectors (ops.add_rmsnorm; rows of up to 256 vectors stay in
+    registers, wider ones take two passes); a d_model that is not a multiple of the vector width takes the module-by-module
+    path."""
     vec = 16 // x.element_size()
-    return x.dtype in (torch.float32, torch.bfloat16, torch.float16) and config.d_model % vec == 0 and config.d_model <= 256 * vec
+    return x.dtype in (torch.float32, torch.bfloat16, torch.float16) and config.d_model % vec == 0
 
 
 @dataclass
@@ -77,8 +78,8 @@ class Mamba(nn.Module):
         if len(self.layers) == 0:
             return x
         if not _fusable_norm(x, self.config):
-            # d_model outside the fused add + RMSNorm kernel's register-resident row (not a multiple of the 16-byte
-            # vector, or wider than 256 vectors): the reference's module-by-module form, same CUDA kernels in the mixer
+            # d_model not a multiple of the fused add + RMSNorm kernels' 16-byte vector: the reference's module-by-module
+            # form, same CUDA kernels in the mixer
             for layer in self.layers:
                 x = layer(x)
             return x

@@ -150,7 +150,8 @@ GFE_API int gfe_ssm_step(const void *u, int64_t u_bs, const void *delta, int64_t
  *   fwd: resid = x + a (a, resid may be NULL: plain RMSNorm of x);  y = (resid * rstd) * w,
  *        rstd[r] = rsqrt(mean(resid[r]^2) + eps)  (fp32, saved for backward; may be NULL for inference)
  *   bwd: dx = dres + d/dresid of the norm (dres may be NULL);  dw[j] = sum_r dy[r,j] * resid[r,j] * rstd[r]
- * D must be a multiple of 16 / sizeof(element) and at most 256 * 16 / sizeof(element).
+ * D must be a multiple of 16 / sizeof(element); rows of up to 256 such vectors are held in registers, wider rows take two
+ * passes (the second from cache).
  */
 GFE_API int gfe_add_rmsnorm_fwd(const void *x, const void *a, const float *w, void *resid, void *y, float *rstd,
                                 int64_t rows, int D, float eps, int dtype, void *stream);

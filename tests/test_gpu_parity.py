@@ -549,7 +549,8 @@ def test_host_pipeline_matches_oracle_and_direct_call(rows):
 # ------------------------------------------------------------------------------- residual add + RMSNorm
 @pytest.mark.parametrize("rows,D,dtype", [(7, 128, torch.float32), (300, 768, torch.float32), (1000, 256, torch.bfloat16),
                                           (33, 1024, torch.float32), (65, 2048, torch.bfloat16), (5, 512, torch.float16),
-                                          (1, 4, torch.float32)])
+                                          (1, 4, torch.float32),
+                                          (70, 4096, torch.float32), (19, 8192, torch.bfloat16), (600, 1028, torch.float32)])   # wider than the register-resident row: two-pass kernels
 @pytest.mark.parametrize("with_add", [True, False])
 def test_add_rmsnorm_vs_torch(rows, D, dtype, with_add):
     """resid = x + a; y = x * rsqrt(mean(x^2) + eps) * w exactly as cross_atten/mamba.py:103 and :408-418, forward and backward
@@ -575,7 +576,8 @@ def test_add_rmsnorm_vs_torch(rows, D, dtype, with_add):
         assert relerr(a.grad, ad.grad) < tol
 
 
-@pytest.mark.parametrize("rows,D,io", [(300, 512, torch.bfloat16), (37, 768, torch.float16), (5, 4, torch.bfloat16)])
+@pytest.mark.parametrize("rows,D,io", [(300, 512, torch.bfloat16), (37, 768, torch.float16), (5, 4, torch.bfloat16),
+                                       (40, 4096, torch.bfloat16)])   # the last one: two-pass kernels
 @pytest.mark.parametrize("with_add", [True, False])
 def test_add_rmsnorm_mixed_dtypes(rows, D, io, with_add):
     """fp32 residual stream with a 16-bit branch (the stack under autocast): resid = x + a in fp32, y in the branch dtype;
