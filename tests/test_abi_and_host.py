@@ -61,6 +61,37 @@ def test_size_queries_without_gpu():
     assert lib.gfe_conv1d_bwd_workspace_bytes(2, 130, 64, 4) == 2 * 2 * 5 * 64 * 4   # B x ceil(L / 128) tiles x (K + 1) x ED fp32
 
 
+def test_independent_segment_workspaces_without_gpu():
+    """Small B * ED: the chained kernels run independent L-segments; the workspace carries one (B, ED, N) aggregate and one
+    (B, ED) sum of delta per segment boundary (size queries assume a 148-SM device when none is present)."""
+    from gfe_mamba_b200 import _native
+    lib = _native.lib()
+    B, L, ED, N = 2, 1858, 1024, 16                 # the production shape: 13 segments of 144 steps in both directions
+    nseg, nblk = 13, ED // 64
+    seg = 256 + (nseg - 1) * B * ED * N * 4 + (nseg - 1) * B * ED * 4
+    assert lib.gfe_selscan_fwd_workspace_bytes(B, L, ED, N) == seg
+    assert lib.gfe_selscan_bwd_workspace_bytes(B, L, ED, N) == seg + nblk * B * L * 32 * 4 + B * nseg * 18 * ED * 4
+    # a 128-channel shard of one 65 536-token sequence: the segment count saturates at 256 (255 boundaries)
+    assert lib.gfe_selscan_fwd_workspace_bytes(1, 65536, 128, N) == 256 + 255 * 128 * N * 4 + 255 * 128 * 4
+    # checkpoints keep the chained layout (every 8 steps) whatever the segment plan
+    assert lib.gfe_selscan_ckpt_bytes(B, L, ED, N) == B * ((L + 7) // 8) * ED * N * 4 + B * L * ED * 4
+
+
+def test_add_rmsnorm_mixed_argument_validation_without_gpu():
+    """The two-dtype entry points reject unsupported pairs and widths before any launch."""
+    from gfe_mamba_b200 import _native
+    lib = _native.lib()
+    fake = ctypes.c_void_p(4096)                     # non-null, 16-byte aligned, never dereferenced on these paths
+    eps = ctypes.c_float(1e-5)
+    assert lib.gfe_add_rmsnorm_fwd_mixed(fake, None, fake, None, fake, None, 5, 64, eps, _native.GFE_BF16, _native.GFE_F32, None) == -2
+    assert b"dtype pair" in lib.gfe_last_error_string()
+    assert lib.gfe_add_rmsnorm_fwd_mixed(fake, None, fake, None, fake, None, 5, 66, eps, _native.GFE_F32, _native.GFE_BF16, None) == -1
+    assert b"multiple of 4" in lib.gfe_last_error_string()
+    assert lib.gfe_add_rmsnorm_fwd_mixed(fake, None, fake, None, fake, None, 0, 64, eps, _native.GFE_F32, _native.GFE_BF16, None) == 0   # no rows: nothing to do
+    assert lib.gfe_add_rmsnorm_bwd_mixed(fake, fake, fake, fake, None, fake, None, fake, 5, 64, _native.GFE_F16, _native.GFE_BF16,
+                                         fake, 1 << 20, None) == -2
+
+
 def test_argument_validation_without_gpu():
     """Bad arguments are rejected before any launch, with a message."""
     from gfe_mamba_b200 import _native
