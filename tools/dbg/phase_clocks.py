@@ -25,7 +25,7 @@ for _ in range(n): step()
 torch.cuda.synchronize()
 warp_chunks = n * B * (ED // 16) * ((L + 15) // 16)     # one warp serves 16 channels
 for name, fn, labels in (("forward", lib.gfe_debug_fwd_phase_clocks, ["unit set-up + chain wait", "barrier (1)", "recurrence (16 steps)", "cp.async wait + barrier (2)", "epilogue", "phase A (items of the next chunk)", "unit tail", "refill (cp.async issue)"]),
-                         ("backward", lib.gfe_debug_bwd_phase_clocks, ["unit set-up + chain wait", "barrier (1)", "sweeps (2 x 8 steps)", "cp.async wait + barrier (2)", "row sums", "phase A (items of the next chunk)", "phase C (warp-local)", "refill (cp.async issue)"])):
+                         ("backward", lib.gfe_debug_bwd_phase_clocks, ["unit set-up + chain wait", "barrier (1)", "fwd sweep 8..15 + (rev 8..15 | fwd 0..7)", "cp.async wait + barrier (2)", "row sums", "phase A (items of the next chunk)", "phase C 8..15 + rev sweep 0..7 + phase C 0..7", "refill (cp.async issue)"])):
     fn(buf, 0)
     tot = sum(buf)
     print(f"{name}: {tot / warp_chunks:.0f} clk per (warp, chunk)")
